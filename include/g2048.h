@@ -1,0 +1,196 @@
+/*
+ * g2048.h — C ABI of the B200-native batched 2048 environment (libg2048.so).
+ *
+ * This is the drop-in boundary for ONE path of rgal/gym-2048: Game2048Env.step()
+ * (+ the reset() it needs for auto-reset) batched over independent boards.  The
+ * reference has no FFI layer of its own (it is pure Python); every entry point
+ * below names the reference method it replaces as `env/envs/game2048_env.py:LINE`
+ * and is what a ctypes/cffi binding in that file would call (INTEGRATION.md shows
+ * the stub).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars.  No torch / CUDA types in any signature;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every pointer of the stateless API is CALLER-OWNED DEVICE memory on the
+ *     current CUDA device; the library allocates nothing persistent there and
+ *     launches asynchronously on `stream` (no implicit synchronisation).
+ *   - return value: 0 on success, a negative G2048_ERR_* otherwise;
+ *     g2048_last_error() gives the text (thread-local).  Nothing throws.
+ *   - board encoding: 16 bytes per board, row-major cell (r,c) at byte 4*r+c,
+ *     each byte the EXPONENT e of the tile value 2^e (0 = empty cell).  Board
+ *     arrays must be 16-byte aligned.  g2048_values_from_exp/exp_from_values
+ *     convert to/from the reference's 4x4 int64 tile VALUES (Matrix).
+ *   - actions: 0=Up 1=Right 2=Down 3=Left (game2048_env.py:210-212).
+ *   - determinism: spawn draws are Philox4x32-10 words addressed by
+ *     (seed, global env id, step index); results do not depend on how the batch
+ *     is sharded over GPUs (env_id_base = global id of element 0).
+ *
+ * Draw stream (frozen, version 1) — see DESIGN.md §3:
+ *   w[0..3] = philox4x32_10(ctr = {idx_lo, idx_hi, env_lo, env_hi | tag<<31},
+ *                           key = {seed_lo, seed_hi})
+ *   tag 0: idx = step_index (g2048_step);   tag 1: idx = reset_index (g2048_reset)
+ *   spawn(board, w): n = #empty cells; p = (uint64)w * n; k = p >> 32;
+ *                    f = (uint32)p;  tile = (f < 3865470567u) ? 2 : 4   [P(2)=0.9]
+ *                    the k-th empty cell in row-major order receives the tile.
+ *   step spawn uses w[0]; a reset (auto-reset in g2048_step, or g2048_reset)
+ *   zeroes the board and spawns with w[1] then w[2].
+ */
+#ifndef G2048_H
+#define G2048_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2048_ABI_VERSION 1
+
+#define G2048_OK            0
+#define G2048_ERR_INVALID  (-1) /* bad argument (NULL required pointer, bad dtype, ...) */
+#define G2048_ERR_ALIGN    (-2) /* board pointer not 16-byte aligned                   */
+#define G2048_ERR_CUDA     (-3) /* CUDA runtime error (text in g2048_last_error)       */
+#define G2048_ERR_NOMEM    (-4) /* allocation failed (stateful API only)               */
+
+/* G2048StepArgs.flags */
+#define G2048_FLAG_AUTO_RESET 1u /* SB3 DummyVecEnv semantics: a terminated env is   */
+                                 /* replaced by a fresh reset() board in the same step */
+
+/* g2048_encode_obs dtype */
+#define G2048_OBS_U8   0
+#define G2048_OBS_F32  1
+#define G2048_OBS_I64  2 /* the reference's dtype (numpy int on Linux) */
+#define G2048_OBS_BF16 3
+
+#define G2048_P2_THRESHOLD 3865470567u /* f < this  <=>  f / 2^32 < 0.9  */
+
+/*
+ * One batched step.  Replaces Game2048Env.step (game2048_env.py:76-100) incl.
+ * move (:194-241), shift (:243-260), add_tile (:166-176), isend (:262-280),
+ * highest (:190-192) and — with G2048_FLAG_AUTO_RESET — reset (:102-111).
+ */
+typedef struct G2048StepArgs {
+  uint8_t*        boards;          /* [n*16] in/out                                        */
+  const uint8_t*  actions;         /* [n]    0..3; only the low 2 bits are read            */
+  float*          rewards;         /* [n]    out: merge score, or illegal_move_reward      */
+  uint8_t*        dones;           /* [n]    out: terminated (0/1)                         */
+  uint8_t*        illegal;         /* [n]    out, nullable: info['illegal_move']           */
+  uint8_t*        highest_exp;     /* [n]    out, nullable: log2(info['highest']) of the   */
+                                   /*        post-spawn (terminal, pre-reset) board        */
+  uint8_t*        legal_mask;      /* [n]    out, nullable: bit d = move d legal on the    */
+                                   /*        board RETURNED in `boards`                    */
+  uint8_t*        terminal_boards; /* [n*16] out, nullable: written only where done        */
+  uint32_t*       ep_score;        /* [n]    in/out, nullable: running episode score       */
+  uint32_t*       ep_len;          /* [n]    in/out, nullable: running episode length      */
+  uint32_t*       final_score;     /* [n]    out, nullable: episode score, where done      */
+  uint32_t*       final_len;       /* [n]    out, nullable: episode length, where done     */
+  const uint32_t* forced_draws;    /* [n*4]  nullable: words used INSTEAD of the Philox    */
+                                   /*        output w[0..3] (fixture / CSV parity)         */
+  uint64_t        n;               /* boards in this call                                  */
+  uint64_t        env_id_base;     /* global env id of element 0                           */
+  uint64_t        seed;            /* Philox key                                           */
+  uint64_t        step_index;      /* Philox counter low 64 bits; caller increments        */
+  float           illegal_move_reward; /* set_illegal_move_reward (:61-67), default 0      */
+  uint32_t        max_tile_exp;    /* set_max_tile (:69-73) as exponent; 0 = None          */
+  uint32_t        flags;           /* G2048_FLAG_*                                         */
+} G2048StepArgs;
+
+int g2048_abi_version(void);
+const char* g2048_last_error(void);
+
+int g2048_step(const G2048StepArgs* args, void* stream);
+
+/*
+ * Game2048Env.reset (game2048_env.py:102-111) for every env whose reset_mask
+ * byte is non-zero (all envs when reset_mask is NULL): zero board + two spawns.
+ */
+int g2048_reset(uint8_t* boards, const uint8_t* reset_mask, uint64_t n,
+                uint64_t env_id_base, uint64_t seed, uint64_t reset_index,
+                void* stream);
+
+/*
+ * Game2048Env.move(direction, trial) (game2048_env.py:194-241) without spawn:
+ * boards_out may alias boards_in (trial=False) or be NULL (trial=True).
+ * changed[i]==0 is the reference's IllegalMove.  scores/changed nullable.
+ */
+int g2048_move(const uint8_t* boards_in, uint8_t* boards_out,
+               const uint8_t* directions, uint32_t* scores, uint8_t* changed,
+               uint64_t n, void* stream);
+
+/*
+ * Board queries: legal-move mask (move(d, trial=True) for d=0..3, :224,236-239),
+ * highest (:190-192) as exponent, number of empties (:186-188), isend (:262-280).
+ * Every output is nullable.
+ */
+int g2048_status(const uint8_t* boards, uint8_t* legal_mask, uint8_t* highest_exp,
+                 uint8_t* n_empty, uint8_t* is_end, uint32_t max_tile_exp,
+                 uint64_t n, void* stream);
+
+/*
+ * stack(flat, layers=15) (game2048_env.py:17-32): one-hot [n,16,4,4], channel 0 =
+ * empty, channel k = (cell == 2^k), k=1..15; a tile >= 2^16 lights no channel.
+ */
+int g2048_encode_obs(const uint8_t* boards, void* obs, int dtype, uint64_t n,
+                     void* stream);
+
+/*
+ * Tile values (reference Matrix, int64) <-> exponents.  exp_from_values counts
+ * cells that are neither 0 nor a power of two 2..2^31 into *bad_count (device
+ * uint32, nullable) and stores 0 for them.
+ */
+int g2048_values_from_exp(const uint8_t* boards, int64_t* values, uint64_t n_cells,
+                          void* stream);
+int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cells,
+                          uint32_t* bad_count, void* stream);
+
+/* Debug: out[4*i..4*i+3] = philox4x32_10(ctr[4*i..], key) — known-answer tests. */
+int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* out,
+                 uint64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Stateful host-buffer API: what a non-CUDA host (the reference's Python, a  */
+/* cgo/JNI caller) binds.  The handle owns the device state for n boards plus */
+/* pinned staging; actions come from and results go to HOST memory.           */
+/* ------------------------------------------------------------------------- */
+typedef struct G2048Env G2048Env;
+
+typedef struct G2048EnvConfig {
+  int32_t  device;               /* CUDA device ordinal                              */
+  uint32_t flags;                /* G2048_FLAG_*                                     */
+  uint64_t n;                    /* boards owned by this handle                      */
+  uint64_t env_id_base;          /* global id of board 0 (sharding)                  */
+  uint64_t seed;
+  float    illegal_move_reward;
+  uint32_t max_tile_exp;
+  uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default */
+  uint32_t reserved;
+} G2048EnvConfig;
+
+/* Host result pointers for g2048_env_step_host; boards/rewards/dones required. */
+typedef struct G2048HostStepOut {
+  uint8_t*  boards;       /* [n*16] */
+  float*    rewards;      /* [n]    */
+  uint8_t*  dones;        /* [n]    */
+  uint8_t*  illegal;      /* [n] nullable */
+  uint8_t*  highest_exp;  /* [n] nullable */
+  uint8_t*  legal_mask;   /* [n] nullable */
+} G2048HostStepOut;
+
+int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg);
+int g2048_env_destroy(G2048Env* env);
+/* reset all boards (advances the handle's reset counter); boards_host nullable */
+int g2048_env_reset_host(G2048Env* env, uint8_t* boards_host);
+/* one step: H2D actions -> kernel -> D2H results, chunk-pipelined; synchronous */
+int g2048_env_step_host(G2048Env* env, const uint8_t* actions_host,
+                        const G2048HostStepOut* out);
+/* device pointers of the handle's state (for zero-copy hosts such as torch)   */
+int g2048_env_device_ptrs(G2048Env* env, uint8_t** boards, float** rewards,
+                          uint8_t** dones);
+int g2048_env_set_boards_host(G2048Env* env, const uint8_t* boards_host);
+uint64_t g2048_env_step_index(const G2048Env* env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2048_H */
