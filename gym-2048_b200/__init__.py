@@ -1,0 +1,20 @@
+"""gym-2048_b200 — B200-native batched 2048 environment (drop-in for rgal/gym-2048's env).
+
+Public surface:
+  BatchedGame2048   N boards on one GPU, one fused CUDA kernel per step (batched.py)
+  HostSteppedEnv    host-buffer handle of the C ABI (actions/results in pinned host memory)
+  Game2048Env       single-env class with the reference's gymnasium + game API (env.py)
+  Game2048VecEnv    Stable-Baselines3-style VecEnv adapter over BatchedGame2048 (vec_env.py)
+  stack, IllegalMove  as in the reference module
+The CUDA extension is built in-tree by `_lib.build()` (nvcc, sm_100a); nothing here has a
+CPU fallback.
+"""
+from . import _lib
+from ._lib import G2048Error, build
+from .batched import ALL_OUTPUTS, BatchedGame2048, HostSteppedEnv, StepResult, shard_range, tile_to_exp
+from .env import Game2048Env, IllegalMove, register, stack
+from .vec_env import Game2048VecEnv
+
+__all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Game2048VecEnv", "IllegalMove",
+           "stack", "register", "shard_range", "tile_to_exp", "build", "G2048Error", "ALL_OUTPUTS"]
+__version__ = "0.1.0"

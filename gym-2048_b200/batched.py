@@ -1,0 +1,345 @@
+"""BatchedGame2048 — N independent 2048 boards stepped by one CUDA kernel per call.
+
+Host-side mirror of the reference env's interface for the batched path
+(`/root/reference/env/envs/game2048_env.py`: reset :102-111, step :76-100, move :194-241,
+isend :262-280, highest :190-192, stack :17-32, set_illegal_move_reward :61-67,
+set_max_tile :69-73), with SB3 `DummyVecEnv` same-step auto-reset.  torch is used only for
+device memory and streams; every game rule runs in libg2048.so (no CPU fallback).
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import FLAG_AUTO_RESET, G2048Error, StepArgs, check
+
+ALL_OUTPUTS = ("illegal", "highest", "legal_mask", "episode", "terminal")
+_OBS_DTYPES = {torch.uint8: _lib.OBS_U8, torch.float32: _lib.OBS_F32, torch.int64: _lib.OBS_I64,
+               torch.bfloat16: _lib.OBS_BF16}
+
+
+def tile_to_exp(max_tile):
+    """set_max_tile value -> exponent for the kernel (0 = None).  A value that no tile can
+    ever equal (not a power of two >= 2) maps to 63, which never matches (`==`, :267)."""
+    if max_tile is None:
+        return 0
+    assert isinstance(max_tile, int), "max_tile must be an int or None"      # :72
+    if max_tile >= 2 and (max_tile & (max_tile - 1)) == 0 and max_tile.bit_length() - 1 < 63:
+        return max_tile.bit_length() - 1
+    return 63
+
+
+def shard_range(total, rank, world):
+    """Contiguous slice [base, base+count) of `total` global env ids owned by `rank`."""
+    per, rem = divmod(int(total), int(world))
+    base = rank * per + min(rank, rem)
+    return base, per + (1 if rank < rem else 0)
+
+
+@dataclass
+class StepResult:
+    boards: torch.Tensor                      # uint8 [n,16] exponents — the env's live state
+    rewards: torch.Tensor                     # float32 [n]
+    dones: torch.Tensor                       # bool [n]
+    illegal: Optional[torch.Tensor] = None    # bool [n]   info['illegal_move']
+    highest_exp: Optional[torch.Tensor] = None  # uint8 [n] log2(info['highest'])
+    legal_mask: Optional[torch.Tensor] = None   # uint8 [n] bit d = move d legal on `boards`
+    terminal_boards: Optional[torch.Tensor] = None  # uint8 [n,16], valid where dones
+    final_score: Optional[torch.Tensor] = None  # int32 [n] episode score, valid where dones
+    final_len: Optional[torch.Tensor] = None    # int32 [n] episode length, valid where dones
+
+
+class BatchedGame2048:
+    """`num_envs` boards resident on one GPU.
+
+    env_id_base is the global id of board 0: draws depend on (seed, global id, step), so a
+    batch sharded over several GPUs/processes reproduces the unsharded result bit for bit.
+    """
+
+    def __init__(self, num_envs, seed=0, device=None, env_id_base=0, illegal_move_reward=0.0,
+                 max_tile=None, auto_reset=True, outputs=ALL_OUTPUTS):
+        if not torch.cuda.is_available():
+            raise G2048Error("BatchedGame2048 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.num_envs = int(num_envs)
+        self.env_id_base = int(env_id_base)
+        self.seed = int(seed) & (2**64 - 1)
+        self.auto_reset = bool(auto_reset)
+        self.step_index = 0
+        self.reset_index = 0
+        self.set_illegal_move_reward(illegal_move_reward)
+        self.set_max_tile(max_tile)
+        unknown = set(outputs) - set(ALL_OUTPUTS)
+        if unknown:
+            raise ValueError("unknown outputs %s" % sorted(unknown))
+        self.outputs = tuple(outputs)
+        n, dev = self.num_envs, self.device
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.boards = torch.zeros((n, 16), **u8)
+        self.rewards = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._dones = torch.zeros(n, **u8)
+        self._illegal = torch.zeros(n, **u8) if "illegal" in outputs else None
+        self.highest_exp = torch.zeros(n, **u8) if "highest" in outputs else None
+        self.legal_mask = torch.zeros(n, **u8) if "legal_mask" in outputs else None
+        self.terminal_boards = torch.zeros((n, 16), **u8) if "terminal" in outputs else None
+        ep = "episode" in outputs
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ep_score = torch.zeros(n, **i32) if ep else None
+        self.ep_len = torch.zeros(n, **i32) if ep else None
+        self.final_score = torch.zeros(n, **i32) if ep else None
+        self.final_len = torch.zeros(n, **i32) if ep else None
+        self._step_counter = None      # device uint64 step index (use_device_step_counter)
+
+    # -- knobs (reference :61-73) ------------------------------------------------------
+    def set_illegal_move_reward(self, reward):
+        self.illegal_move_reward = float(reward)
+        self.reward_range = (self.illegal_move_reward, float(2 ** 16))
+
+    def set_max_tile(self, max_tile):
+        self.max_tile = max_tile
+        self.max_tile_exp = tile_to_exp(max_tile)
+
+    # -- helpers -----------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _as_u8(self, x, shape, what):
+        t = torch.as_tensor(x)
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+        if t.dtype != torch.uint8:
+            t = t.to(torch.int64)
+            if what == "actions" and t.numel() and (int(t.min()) < 0 or int(t.max()) > 3):
+                raise ValueError("actions must be in {0,1,2,3} (Discrete(4))")
+            t = t.to(torch.uint8)
+        t = t.to(self.device).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(t.shape)))
+        return t
+
+    # -- reset (:102-111) --------------------------------------------------------------
+    def reset(self, seed=None, mask=None):
+        """Fresh boards (two spawned tiles) for all envs, or those where `mask` is set.
+        A `seed` re-keys the draw stream and restarts its counters (reset(seed), :103)."""
+        if seed is not None:
+            self.seed = int(seed) & (2**64 - 1)
+            self.step_index = 0
+            self.reset_index = 0
+            if self._step_counter is not None:
+                self._step_counter.zero_()
+        m = None if mask is None else self._as_u8(mask, (self.num_envs,), "mask")
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_reset(self._ptr(self.boards), self._ptr(m), self.num_envs, self.env_id_base,
+                                       self.seed, self.reset_index, self._stream()))
+        self.reset_index += 1
+        if self.ep_score is not None:
+            if m is None:
+                self.ep_score.zero_()
+                self.ep_len.zero_()
+            else:
+                keep = (m == 0).to(torch.int32)
+                self.ep_score.mul_(keep)
+                self.ep_len.mul_(keep)
+        if self.legal_mask is not None:
+            self.status(legal_mask=self.legal_mask)
+        return self.boards
+
+    # -- step (:76-100) ----------------------------------------------------------------
+    def step(self, actions, forced_draws=None):
+        """One env step for every board.  `actions`: uint8/int tensor [n] on any device."""
+        n = self.num_envs
+        if isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device \
+                and actions.is_contiguous() and actions.shape == (n,):
+            act = actions                       # fast path: no validation pass over the batch
+        else:
+            act = self._as_u8(actions, (n,), "actions")
+        fd = None
+        if forced_draws is not None:
+            fd = torch.as_tensor(forced_draws).to(self.device).contiguous()
+            if fd.dtype != torch.uint32 or tuple(fd.shape) != (n, 4):
+                raise ValueError("forced_draws must be uint32 [n,4]")
+        a = StepArgs(self._ptr(self.boards), self._ptr(act), self._ptr(self.rewards), self._ptr(self._dones),
+                     self._ptr(self._illegal), self._ptr(self.highest_exp), self._ptr(self.legal_mask),
+                     self._ptr(self.terminal_boards), self._ptr(self.ep_score), self._ptr(self.ep_len),
+                     self._ptr(self.final_score), self._ptr(self.final_len), self._ptr(fd), self._ptr(self._step_counter),
+                     n, self.env_id_base, self.seed, self.step_index,
+                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_step(C.byref(a), self._stream()))
+        self.step_index += 1      # host mirror; the device counter (if any) is bumped on the stream
+        return StepResult(self.boards, self.rewards, self._dones.view(torch.bool),
+                          None if self._illegal is None else self._illegal.view(torch.bool),
+                          self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
+                          self.final_len)
+
+    def use_device_step_counter(self, enable=True):
+        """Keep the step index in device memory (bumped by a 1-thread kernel after each step) so
+        a loop of step() calls can be captured once in a CUDA graph and replayed: with the
+        default host-side index every replay would reuse the captured step's draws."""
+        if enable:
+            self._step_counter = torch.tensor([self.step_index], dtype=torch.int64, device=self.device)
+        else:
+            if self._step_counter is not None:
+                self.step_index = int(self._step_counter.item())
+            self._step_counter = None
+
+    # -- move / status -----------------------------------------------------------------
+    def move(self, directions, trial=False):
+        """Game2048Env.move for every board (no spawn).  Returns (scores int32 [n], changed bool [n]);
+        changed == False is the reference's IllegalMove.  trial=True leaves the boards untouched."""
+        d = self._as_u8(directions, (self.num_envs,), "actions")
+        scores = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        changed = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_move(self._ptr(self.boards), None if trial else self._ptr(self.boards),
+                                      self._ptr(d), self._ptr(scores), self._ptr(changed), self.num_envs,
+                                      self._stream()))
+        return scores, changed.view(torch.bool)
+
+    def status(self, legal_mask=None):
+        """legal-move mask, highest exponent, number of empties and isend() of the current boards."""
+        n = self.num_envs
+        mk = lambda: torch.zeros(n, dtype=torch.uint8, device=self.device)     # noqa: E731
+        lm = mk() if legal_mask is None else legal_mask
+        hi, ne, end = mk(), mk(), mk()
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_status(self._ptr(self.boards), self._ptr(lm), self._ptr(hi), self._ptr(ne),
+                                        self._ptr(end), self.max_tile_exp, n, self._stream()))
+        return dict(legal_mask=lm, highest_exp=hi, n_empty=ne, is_end=end.view(torch.bool))
+
+    # -- observations (stack, :17-32) ----------------------------------------------------
+    def observe(self, dtype=torch.uint8, out=None, boards=None):
+        """One-hot [n,16,4,4] of `boards` (default: the live boards) in the reference's
+        channel convention; dtype uint8 / float32 / bfloat16 / int64 (the reference's)."""
+        if dtype not in _OBS_DTYPES:
+            raise ValueError("unsupported obs dtype %s" % dtype)
+        b = self.boards if boards is None else boards
+        n = b.shape[0]
+        if out is None:
+            out = torch.empty((n, 16, 4, 4), dtype=dtype, device=self.device)
+        elif out.dtype != dtype or tuple(out.shape) != (n, 16, 4, 4) or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor of shape %s" % (dtype, (n, 16, 4, 4)))
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_encode_obs(self._ptr(b), self._ptr(out), _OBS_DTYPES[dtype], n, self._stream()))
+        return out
+
+    # -- tile values <-> exponents -------------------------------------------------------
+    def board_values(self, boards=None):
+        """int64 [n,4,4] tile values (the reference's Matrix)."""
+        b = self.boards if boards is None else boards
+        out = torch.empty((b.shape[0], 4, 4), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_values_from_exp(self._ptr(b), self._ptr(out), b.numel(), self._stream()))
+        return out
+
+    def set_board_values(self, values):
+        """Load boards given as tile values (0, 2, 4, ...), shape [n,4,4] or [n,16]."""
+        v = torch.as_tensor(values).to(torch.int64).to(self.device).contiguous()
+        if v.numel() != self.num_envs * 16:
+            raise ValueError("expected %d cells, got %d" % (self.num_envs * 16, v.numel()))
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_exp_from_values(self._ptr(v), self._ptr(self.boards), v.numel(), self._ptr(bad),
+                                                 self._stream()))
+        if int(bad.item()):
+            raise ValueError("%d cells are not 0 or a power of two in 2..2^31" % int(bad.item()))
+        if self.legal_mask is not None:
+            self.status(legal_mask=self.legal_mask)
+
+    def set_boards(self, exps):
+        self.boards.copy_(self._as_u8(exps, (self.num_envs, 16), "boards"))
+        if self.legal_mask is not None:
+            self.status(legal_mask=self.legal_mask)
+
+    # -- checkpoint / resume -------------------------------------------------------------
+    def state_dict(self):
+        if self._step_counter is not None:
+            self.step_index = int(self._step_counter.item())
+        sd = dict(boards=self.boards.clone(), seed=self.seed, step_index=self.step_index,
+                  reset_index=self.reset_index, env_id_base=self.env_id_base)
+        if self.ep_score is not None:
+            sd.update(ep_score=self.ep_score.clone(), ep_len=self.ep_len.clone())
+        return sd
+
+    def load_state_dict(self, sd):
+        self.boards.copy_(sd["boards"])
+        self.seed, self.step_index, self.reset_index = int(sd["seed"]), int(sd["step_index"]), int(sd["reset_index"])
+        self.env_id_base = int(sd["env_id_base"])
+        if self._step_counter is not None:
+            self._step_counter.fill_(self.step_index)
+        if self.ep_score is not None and "ep_score" in sd:
+            self.ep_score.copy_(sd["ep_score"])
+            self.ep_len.copy_(sd["ep_len"])
+        if self.legal_mask is not None:
+            self.status(legal_mask=self.legal_mask)
+
+
+class HostBuffers:
+    """Pinned host arrays for HostSteppedEnv (numpy views over torch pinned memory)."""
+
+    def __init__(self, n, extras=False):
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()       # noqa: E731
+        self.actions = pin((n,), torch.uint8)
+        self.boards = pin((n, 16), torch.uint8)
+        self.rewards = pin((n,), torch.float32)
+        self.dones = pin((n,), torch.uint8)
+        self.illegal = pin((n,), torch.uint8) if extras else None
+        self.highest_exp = pin((n,), torch.uint8) if extras else None
+        self.legal_mask = pin((n,), torch.uint8) if extras else None
+
+
+class HostSteppedEnv:
+    """The stateful host-buffer handle of the C ABI (g2048_env_*): actions come from HOST
+    memory and boards/rewards/dones land in HOST memory every step, with the host<->device
+    copies chunk-pipelined against the kernel inside the library.  This is the call a
+    CPU-side caller (the reference's numpy world) makes; bench.py times it as `e2e`."""
+
+    def __init__(self, num_envs, seed=0, device=0, env_id_base=0, illegal_move_reward=0.0, max_tile=None,
+                 auto_reset=True, n_chunks=0, extras=False):
+        self.lib = _lib.lib()
+        self.num_envs = int(num_envs)
+        cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
+                             int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
+                             int(n_chunks), 0)
+        self._h = C.c_void_p()
+        check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
+        self.buffers = HostBuffers(self.num_envs, extras)
+        b = self.buffers
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())          # noqa: E731
+        self._out = _lib.HostStepOut(p(b.boards), p(b.rewards), p(b.dones), p(b.illegal), p(b.highest_exp),
+                                     p(b.legal_mask))
+
+    def reset(self):
+        check(self.lib.g2048_env_reset_host(self._h, C.c_void_p(self.buffers.boards.data_ptr())))
+        return self.buffers.boards
+
+    def step(self, actions=None):
+        """actions: None (already written into buffers.actions) or a uint8 array/tensor [n]."""
+        if actions is not None:
+            self.buffers.actions.copy_(torch.as_tensor(actions, dtype=torch.uint8))
+        check(self.lib.g2048_env_step_host(self._h, C.c_void_p(self.buffers.actions.data_ptr()),
+                                           C.byref(self._out)))
+        return self.buffers
+
+    @property
+    def step_index(self):
+        return int(self.lib.g2048_env_step_index(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.g2048_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

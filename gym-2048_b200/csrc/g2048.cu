@@ -1,0 +1,567 @@
+// g2048.cu — CUDA kernels (sm_100a) and the C ABI of libg2048.so (include/g2048.h).
+//
+// The hot path is g2048_step_kernel: one board per lane, the 16-byte board held in four
+// registers, one coalesced 128-bit load and store per board, every game rule evaluated
+// branch-free with byte-SIMD integer ops (g2048_device.cuh).  Pure integer/indexing work:
+// HBM- and issue-bound, no tensor cores.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/g2048.h"
+#include "g2048_device.cuh"
+
+namespace g2048 {
+
+// ------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(G2048_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+#define G2048_CUDA(call)                                  \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// launch geometry: 256-thread CTAs, grid-stride, at most kCtasPerSm resident CTAs per SM
+// so large batches run as one persistent wave over the 148 SMs.
+// ------------------------------------------------------------------------------------
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 8;
+
+static int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+    cached_dev = dev;
+  }
+  return cached;
+}
+static unsigned grid_for(uint64_t n) {
+  const uint64_t need = (n + kThreads - 1) / kThreads;
+  const uint64_t cap = (uint64_t)sm_count() * kCtasPerSm;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------
+struct StepParams {
+  uint4* boards;
+  const uint8_t* actions;
+  float* rewards;
+  uint8_t* dones;
+  uint8_t* illegal;
+  uint8_t* highest_exp;
+  uint8_t* legal_mask;
+  uint4* terminal_boards;
+  uint32_t* ep_score;
+  uint32_t* ep_len;
+  uint32_t* final_score;
+  uint32_t* final_len;
+  const uint4* forced_draws;
+  const uint64_t* step_counter;
+  uint64_t n, env_id_base, seed, step_index;
+  float illegal_move_reward;
+  uint32_t max_tile_exp;
+  uint32_t flags;
+};
+
+// Game2048Env.step (:76-100) for n boards.  EXTRAS=false is the lean variant used when
+// none of the optional outputs/inputs is requested (boards, actions, rewards, dones only).
+template <bool EXTRAS>
+__global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p) {
+  const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  const uint64_t step_index = p.step_counter ? *p.step_counter : p.step_index;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += stride) {
+    uint4 bd = p.boards[i];
+    const uint32_t action = p.actions[i] & 3u;
+    Words w;
+    if (EXTRAS && p.forced_draws) {
+      const uint4 f = p.forced_draws[i];
+      w = Words{f.x, f.y, f.z, f.w};
+    } else {
+      w = draw_words(p.seed, p.env_id_base + i, step_index, 0u);
+    }
+    const StepOut o = step_board(bd.x, bd.y, bd.z, bd.w, action, w, p.max_tile_exp,
+                                 EXTRAS && p.highest_exp != nullptr, auto_reset);
+    p.boards[i] = bd;
+    p.rewards[i] = o.legal ? (float)o.score : p.illegal_move_reward;   // :90 / :95
+    p.dones[i] = o.done ? 1 : 0;
+    if (EXTRAS) {
+      if (p.illegal) p.illegal[i] = o.legal ? 0 : 1;                   // :82, :93
+      if (p.highest_exp) p.highest_exp[i] = (uint8_t)o.highest;        // :97
+      uint32_t es = 0, el = 0;
+      if (p.ep_score) es = p.ep_score[i] + o.score;                    // :86
+      if (p.ep_len) el = p.ep_len[i] + 1u;
+      if (o.done) {
+        if (p.terminal_boards) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
+        if (p.final_score) p.final_score[i] = es;
+        if (p.final_len) p.final_len[i] = el;
+        if (auto_reset) es = el = 0u;
+      }
+      if (p.ep_score) p.ep_score[i] = es;
+      if (p.ep_len) p.ep_len[i] = el;
+      if (p.legal_mask) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
+    }
+  }
+}
+
+__global__ void g2048_bump_counter_kernel(uint64_t* counter) { *counter += 1ull; }
+
+// Game2048Env.reset (:102-111)
+__global__ void __launch_bounds__(kThreads)
+g2048_reset_kernel(uint4* boards, const uint8_t* reset_mask, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                   uint64_t reset_index) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    if (reset_mask && !reset_mask[i]) continue;
+    const Words w = draw_words(seed, env_id_base + i, reset_index, 1u);
+    uint4 bd;
+    fresh_board(w.w1, w.w2, bd.x, bd.y, bd.z, bd.w);
+    boards[i] = bd;
+  }
+}
+
+// Game2048Env.add_tile (:166-176)
+__global__ void __launch_bounds__(kThreads)
+g2048_add_tile_kernel(uint4* boards, uint64_t n, uint64_t env_id_base, uint64_t seed, uint64_t step_index) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint4 bd = boards[i];
+    const Words w = draw_words(seed, env_id_base + i, step_index, 0u);
+    spawn(bd.x, bd.y, bd.z, bd.w, w.w0);
+    boards[i] = bd;
+  }
+}
+
+// Game2048Env.move(direction, trial) (:194-241), no spawn
+__global__ void __launch_bounds__(kThreads)
+g2048_move_kernel(const uint4* in, uint4* out, const uint8_t* directions, uint32_t* scores, uint8_t* changed,
+                  uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint4 bd = in[i];
+    const uint32_t act = directions[i] & 3u;
+    uint32_t a, b, c, d;
+    orient(kOrientIn[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+    const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
+    const uint32_t s = slide_merge(a, b, c, d);
+    orient(kOrientOut[act], a, b, c, d, bd.x, bd.y, bd.z, bd.w);
+    if (out) out[i] = bd;
+    if (scores) scores[i] = s;
+    if (changed) changed[i] = (((a ^ a0) | (b ^ b0)) | ((c ^ c0) | (d ^ d0))) != 0u ? 1 : 0;
+  }
+}
+
+// legal mask / highest / empties / isend (:186-192, :262-280)
+__global__ void __launch_bounds__(kThreads)
+g2048_status_kernel(const uint4* boards, uint8_t* lm, uint8_t* hi, uint8_t* ne, uint8_t* is_end,
+                    uint32_t max_tile_exp, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint4 bd = boards[i];
+    const uint32_t empties = count_empty(bd.x, bd.y, bd.z, bd.w);
+    const uint32_t h = highest_exp(bd.x, bd.y, bd.z, bd.w);
+    if (lm) lm[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
+    if (hi) hi[i] = (uint8_t)h;
+    if (ne) ne[i] = (uint8_t)empties;
+    if (is_end)
+      is_end[i] = ((max_tile_exp != 0u && h == max_tile_exp) ||
+                   (empties == 0u && full_board_is_dead(bd.x, bd.y, bd.z, bd.w))) ? 1 : 0;
+  }
+}
+
+// stack() (:17-32): obs[n][16][4][4]; one thread per (board, channel, row) writes the four
+// cells of that row, so consecutive threads write consecutive addresses for every dtype.
+template <typename T> struct Obs4;
+template <> struct Obs4<uint8_t> {
+  static __device__ __forceinline__ void store(uint8_t* o, uint64_t t, uint32_t f) {   // f: 0/1 per byte
+    reinterpret_cast<uint32_t*>(o)[t] = f;
+  }
+};
+template <> struct Obs4<float> {
+  static __device__ __forceinline__ void store(float* o, uint64_t t, uint32_t f) {
+    reinterpret_cast<float4*>(o)[t] = make_float4((float)(f & 1u), (float)((f >> 8) & 1u),
+                                                  (float)((f >> 16) & 1u), (float)(f >> 24));
+  }
+};
+template <> struct Obs4<int64_t> {
+  static __device__ __forceinline__ void store(int64_t* o, uint64_t t, uint32_t f) {
+    longlong2* q = reinterpret_cast<longlong2*>(o) + 2 * t;
+    q[0] = make_longlong2((long long)(f & 1u), (long long)((f >> 8) & 1u));
+    q[1] = make_longlong2((long long)((f >> 16) & 1u), (long long)(f >> 24));
+  }
+};
+struct bf16x4 { uint32_t lo, hi; };
+template <> struct Obs4<bf16x4> {
+  static __device__ __forceinline__ void store(bf16x4* o, uint64_t t, uint32_t f) {   // bf16 1.0 = 0x3F80
+    uint2 v;
+    v.x = ((f & 1u) * 0x3F80u) | (((f >> 8) & 1u) * 0x3F800000u);
+    v.y = (((f >> 16) & 1u) * 0x3F80u) | ((f >> 24) * 0x3F800000u);
+    reinterpret_cast<uint2*>(o)[t] = v;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) g2048_obs_kernel(const uint32_t* boards, T* obs, uint64_t n_rows64) {
+  // t enumerates (board, channel, row): board = t / 64, channel = (t / 4) % 16, row = t % 4
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x; t < n_rows64; t += stride) {
+    const uint32_t row = (uint32_t)t & 3u, ch = ((uint32_t)t >> 2) & 15u;
+    const uint32_t r = boards[(t >> 6) * 4 + row];
+    // byte == ch (exponents >= 16 match no channel, :28-30; ch 0 = empty, :25)
+    const uint32_t eq = (~((r ^ (ch * K1)) + L7) & H) >> 7;
+    Obs4<T>::store(obs, t, eq);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+g2048_values_from_exp_kernel(const uint8_t* exps, int64_t* values, uint64_t n_cells) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_cells; i += stride) {
+    const uint32_t e = exps[i];
+    values[i] = e ? (int64_t)(1ull << (e & 63u)) : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+g2048_exp_from_values_kernel(const int64_t* values, uint8_t* exps, uint64_t n_cells, uint32_t* bad_count) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_cells; i += stride) {
+    const int64_t v = values[i];
+    uint32_t e = 0;
+    if (v != 0) {
+      const bool ok = v >= 2 && v <= (1ll << 31) && (v & (v - 1)) == 0;
+      if (ok) e = 63u - (uint32_t)__clzll(v);
+      else if (bad_count) atomicAdd(bad_count, 1u);
+    }
+    exps[i] = (uint8_t)e;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+g2048_philox_kernel(const uint4* ctr, uint32_t k0, uint32_t k1, uint4* out, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint4 c = ctr[i];
+    const Words w = philox4x32_10(c.x, c.y, c.z, c.w, k0, k1);
+    out[i] = make_uint4(w.w0, w.w1, w.w2, w.w3);
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int launch_check(const char* name) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  return G2048_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// stateful host-buffer environment
+// ------------------------------------------------------------------------------------
+}  // namespace g2048
+
+struct G2048Env {
+  G2048EnvConfig cfg;
+  uint64_t step_index, reset_index;
+  uint32_t n_chunks;
+  // device state / results
+  uint8_t* d_boards;
+  uint8_t* d_actions;
+  float* d_rewards;
+  uint8_t* d_dones;
+  uint8_t* d_illegal;
+  uint8_t* d_highest;
+  uint8_t* d_mask;
+  uint32_t* d_ep_score;
+  uint32_t* d_ep_len;
+  cudaStream_t streams[4];
+  int n_streams;
+};
+
+using namespace g2048;
+
+extern "C" {
+
+int g2048_abi_version(void) { return G2048_ABI_VERSION; }
+const char* g2048_last_error(void) { return g_err; }
+
+int g2048_step(const G2048StepArgs* a, void* stream) {
+  if (!a) return fail(G2048_ERR_INVALID, "g2048_step: args is NULL");
+  if (a->n == 0) return G2048_OK;
+  if (!a->boards || !a->actions || !a->rewards || !a->dones)
+    return fail(G2048_ERR_INVALID, "g2048_step: boards, actions, rewards and dones are required");
+  if (!aligned16(a->boards) || !aligned16(a->terminal_boards) || !aligned16(a->forced_draws))
+    return fail(G2048_ERR_ALIGN, "g2048_step: boards / terminal_boards / forced_draws must be 16-byte aligned");
+  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
+  StepParams p;
+  p.boards = reinterpret_cast<uint4*>(a->boards);
+  p.actions = a->actions;
+  p.rewards = a->rewards;
+  p.dones = a->dones;
+  p.illegal = a->illegal;
+  p.highest_exp = a->highest_exp;
+  p.legal_mask = a->legal_mask;
+  p.terminal_boards = reinterpret_cast<uint4*>(a->terminal_boards);
+  p.ep_score = a->ep_score;
+  p.ep_len = a->ep_len;
+  p.final_score = a->final_score;
+  p.final_len = a->final_len;
+  p.forced_draws = reinterpret_cast<const uint4*>(a->forced_draws);
+  p.step_counter = a->step_counter;
+  p.n = a->n;
+  p.env_id_base = a->env_id_base;
+  p.seed = a->seed;
+  p.step_index = a->step_index;
+  p.illegal_move_reward = a->illegal_move_reward;
+  p.max_tile_exp = a->max_tile_exp;
+  p.flags = a->flags;
+  const bool extras = a->illegal || a->highest_exp || a->legal_mask || a->terminal_boards || a->ep_score ||
+                      a->ep_len || a->final_score || a->final_len || a->forced_draws;
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (extras) g2048_step_kernel<true><<<grid_for(a->n), kThreads, 0, s>>>(p);
+  else        g2048_step_kernel<false><<<grid_for(a->n), kThreads, 0, s>>>(p);
+  if (a->step_counter) g2048_bump_counter_kernel<<<1, 1, 0, s>>>(a->step_counter);
+  return launch_check("g2048_step_kernel");
+}
+
+int g2048_reset(uint8_t* boards, const uint8_t* reset_mask, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                uint64_t reset_index, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!boards) return fail(G2048_ERR_INVALID, "g2048_reset: boards is NULL");
+  if (!aligned16(boards)) return fail(G2048_ERR_ALIGN, "g2048_reset: boards must be 16-byte aligned");
+  g2048_reset_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(boards), reset_mask, n, env_id_base, seed, reset_index);
+  return launch_check("g2048_reset_kernel");
+}
+
+int g2048_add_tile(uint8_t* boards, uint64_t n, uint64_t env_id_base, uint64_t seed, uint64_t step_index,
+                   void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!boards) return fail(G2048_ERR_INVALID, "g2048_add_tile: boards is NULL");
+  if (!aligned16(boards)) return fail(G2048_ERR_ALIGN, "g2048_add_tile: boards must be 16-byte aligned");
+  g2048_add_tile_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(boards), n, env_id_base, seed, step_index);
+  return launch_check("g2048_add_tile_kernel");
+}
+
+int g2048_move(const uint8_t* boards_in, uint8_t* boards_out, const uint8_t* directions, uint32_t* scores,
+               uint8_t* changed, uint64_t n, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!boards_in || !directions) return fail(G2048_ERR_INVALID, "g2048_move: boards_in and directions are required");
+  if (!aligned16(boards_in) || !aligned16(boards_out))
+    return fail(G2048_ERR_ALIGN, "g2048_move: boards must be 16-byte aligned");
+  g2048_move_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(boards_in), reinterpret_cast<uint4*>(boards_out), directions, scores,
+      changed, n);
+  return launch_check("g2048_move_kernel");
+}
+
+int g2048_status(const uint8_t* boards, uint8_t* legal_mask_out, uint8_t* highest_out, uint8_t* n_empty,
+                 uint8_t* is_end, uint32_t max_tile_exp, uint64_t n, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!boards) return fail(G2048_ERR_INVALID, "g2048_status: boards is NULL");
+  if (!aligned16(boards)) return fail(G2048_ERR_ALIGN, "g2048_status: boards must be 16-byte aligned");
+  g2048_status_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(boards), legal_mask_out, highest_out, n_empty, is_end, max_tile_exp, n);
+  return launch_check("g2048_status_kernel");
+}
+
+int g2048_encode_obs(const uint8_t* boards, void* obs, int dtype, uint64_t n, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!boards || !obs) return fail(G2048_ERR_INVALID, "g2048_encode_obs: boards and obs are required");
+  if (!aligned16(boards) || !aligned16(obs))
+    return fail(G2048_ERR_ALIGN, "g2048_encode_obs: boards and obs must be 16-byte aligned");
+  const uint64_t t = n * 64;
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(boards);
+  switch (dtype) {
+    case G2048_OBS_U8:   g2048_obs_kernel<uint8_t><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<uint8_t*>(obs), t); break;
+    case G2048_OBS_F32:  g2048_obs_kernel<float><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<float*>(obs), t); break;
+    case G2048_OBS_I64:  g2048_obs_kernel<int64_t><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<int64_t*>(obs), t); break;
+    case G2048_OBS_BF16: g2048_obs_kernel<bf16x4><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<bf16x4*>(obs), t); break;
+    default: return fail(G2048_ERR_INVALID, "g2048_encode_obs: unknown dtype %d", dtype);
+  }
+  return launch_check("g2048_obs_kernel");
+}
+
+int g2048_values_from_exp(const uint8_t* boards, int64_t* values, uint64_t n_cells, void* stream) {
+  if (n_cells == 0) return G2048_OK;
+  if (!boards || !values) return fail(G2048_ERR_INVALID, "g2048_values_from_exp: NULL pointer");
+  g2048_values_from_exp_kernel<<<grid_for(n_cells), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      boards, values, n_cells);
+  return launch_check("g2048_values_from_exp_kernel");
+}
+
+int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cells, uint32_t* bad_count,
+                          void* stream) {
+  if (n_cells == 0) return G2048_OK;
+  if (!boards || !values) return fail(G2048_ERR_INVALID, "g2048_exp_from_values: NULL pointer");
+  g2048_exp_from_values_kernel<<<grid_for(n_cells), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      values, boards, n_cells, bad_count);
+  return launch_check("g2048_exp_from_values_kernel");
+}
+
+int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* out, uint64_t n, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!ctr || !out) return fail(G2048_ERR_INVALID, "g2048_philox: NULL pointer");
+  if (!aligned16(ctr) || !aligned16(out)) return fail(G2048_ERR_ALIGN, "g2048_philox: 16-byte alignment required");
+  g2048_philox_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(ctr), key0, key1, reinterpret_cast<uint4*>(out), n);
+  return launch_check("g2048_philox_kernel");
+}
+
+// ---- stateful host-buffer API ---------------------------------------------------------
+
+int g2048_env_destroy(G2048Env* e) {
+  if (!e) return G2048_OK;
+  cudaSetDevice(e->cfg.device);
+  for (int i = 0; i < e->n_streams; ++i) cudaStreamDestroy(e->streams[i]);
+  cudaFree(e->d_boards); cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_dones);
+  cudaFree(e->d_illegal); cudaFree(e->d_highest); cudaFree(e->d_mask);
+  cudaFree(e->d_ep_score); cudaFree(e->d_ep_len);
+  delete e;
+  return G2048_OK;
+}
+
+int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
+  if (!out || !cfg) return fail(G2048_ERR_INVALID, "g2048_env_create: NULL argument");
+  if (cfg->n == 0) return fail(G2048_ERR_INVALID, "g2048_env_create: n must be > 0");
+  if (cfg->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_env_create: max_tile_exp > 63");
+  G2048_CUDA(cudaSetDevice(cfg->device));
+  G2048Env* e = new (std::nothrow) G2048Env();
+  if (!e) return fail(G2048_ERR_NOMEM, "g2048_env_create: out of host memory");
+  std::memset(e, 0, sizeof *e);
+  e->cfg = *cfg;
+  e->n_chunks = cfg->n_chunks ? cfg->n_chunks : 4u;
+  if (e->n_chunks > 64u) e->n_chunks = 64u;
+  const uint64_t n = cfg->n;
+  cudaError_t err = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes); };
+  alloc((void**)&e->d_boards, n * 16); alloc((void**)&e->d_actions, n); alloc((void**)&e->d_rewards, n * 4);
+  alloc((void**)&e->d_dones, n); alloc((void**)&e->d_illegal, n); alloc((void**)&e->d_highest, n);
+  alloc((void**)&e->d_mask, n); alloc((void**)&e->d_ep_score, n * 4); alloc((void**)&e->d_ep_len, n * 4);
+  if (err == cudaSuccess) err = cudaMemset(e->d_ep_score, 0, n * 4);
+  if (err == cudaSuccess) err = cudaMemset(e->d_ep_len, 0, n * 4);
+  if (err == cudaSuccess) err = cudaMemset(e->d_boards, 0, n * 16);
+  for (int i = 0; i < 4 && err == cudaSuccess; ++i) {
+    err = cudaStreamCreateWithFlags(&e->streams[i], cudaStreamNonBlocking);
+    if (err == cudaSuccess) e->n_streams = i + 1;
+  }
+  if (err != cudaSuccess) {
+    const int rc = err == cudaErrorMemoryAllocation ? fail(G2048_ERR_NOMEM, "g2048_env_create: %s", cudaGetErrorString(err))
+                                                    : cuda_fail(err, "g2048_env_create");
+    g2048_env_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return G2048_OK;
+}
+
+static int env_sync(G2048Env* e) {
+  for (int i = 0; i < e->n_streams; ++i) G2048_CUDA(cudaStreamSynchronize(e->streams[i]));
+  return G2048_OK;
+}
+
+int g2048_env_reset_host(G2048Env* e, uint8_t* boards_host) {
+  if (!e) return fail(G2048_ERR_INVALID, "g2048_env_reset_host: env is NULL");
+  G2048_CUDA(cudaSetDevice(e->cfg.device));
+  const cudaStream_t s = e->streams[0];
+  int rc = g2048_reset(e->d_boards, nullptr, e->cfg.n, e->cfg.env_id_base, e->cfg.seed, e->reset_index, s);
+  if (rc) return rc;
+  e->reset_index += 1;
+  G2048_CUDA(cudaMemsetAsync(e->d_ep_score, 0, e->cfg.n * 4, s));
+  G2048_CUDA(cudaMemsetAsync(e->d_ep_len, 0, e->cfg.n * 4, s));
+  if (boards_host) G2048_CUDA(cudaMemcpyAsync(boards_host, e->d_boards, e->cfg.n * 16, cudaMemcpyDeviceToHost, s));
+  G2048_CUDA(cudaStreamSynchronize(s));
+  return G2048_OK;
+}
+
+int g2048_env_set_boards_host(G2048Env* e, const uint8_t* boards_host) {
+  if (!e || !boards_host) return fail(G2048_ERR_INVALID, "g2048_env_set_boards_host: NULL argument");
+  G2048_CUDA(cudaSetDevice(e->cfg.device));
+  G2048_CUDA(cudaMemcpyAsync(e->d_boards, boards_host, e->cfg.n * 16, cudaMemcpyHostToDevice, e->streams[0]));
+  G2048_CUDA(cudaStreamSynchronize(e->streams[0]));
+  return G2048_OK;
+}
+
+// One step with HOST buffers.  The batch is cut into n_chunks slices of a multiple of 256
+// boards; slice c runs H2D(actions) -> step kernel -> D2H(results) on stream c % n_streams,
+// so the PCIe copies of one slice overlap the kernel and the opposite-direction copies of
+// its neighbours.  Pinned caller buffers (cudaHostAlloc / cudaHostRegister) get full DMA
+// speed; pageable ones work but are staged by the driver.
+int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048HostStepOut* o) {
+  if (!e || !actions_host || !o) return fail(G2048_ERR_INVALID, "g2048_env_step_host: NULL argument");
+  if (!o->boards || !o->rewards || !o->dones)
+    return fail(G2048_ERR_INVALID, "g2048_env_step_host: boards, rewards and dones are required");
+  G2048_CUDA(cudaSetDevice(e->cfg.device));
+  const uint64_t n = e->cfg.n;
+  uint64_t per = (n + e->n_chunks - 1) / e->n_chunks;
+  per = (per + 255) / 256 * 256;
+  int c = 0;
+  for (uint64_t lo = 0; lo < n; lo += per, ++c) {
+    const uint64_t m = (n - lo < per) ? n - lo : per;
+    const cudaStream_t s = e->streams[c % e->n_streams];
+    G2048_CUDA(cudaMemcpyAsync(e->d_actions + lo, actions_host + lo, m, cudaMemcpyHostToDevice, s));
+    G2048StepArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.boards = e->d_boards + 16 * lo;
+    a.actions = e->d_actions + lo;
+    a.rewards = e->d_rewards + lo;
+    a.dones = e->d_dones + lo;
+    a.illegal = o->illegal ? e->d_illegal + lo : nullptr;
+    a.highest_exp = o->highest_exp ? e->d_highest + lo : nullptr;
+    a.legal_mask = o->legal_mask ? e->d_mask + lo : nullptr;
+    a.ep_score = e->d_ep_score + lo;
+    a.ep_len = e->d_ep_len + lo;
+    a.n = m;
+    a.env_id_base = e->cfg.env_id_base + lo;
+    a.seed = e->cfg.seed;
+    a.step_index = e->step_index;
+    a.illegal_move_reward = e->cfg.illegal_move_reward;
+    a.max_tile_exp = e->cfg.max_tile_exp;
+    a.flags = e->cfg.flags;
+    const int rc = g2048_step(&a, s);
+    if (rc) return rc;
+    G2048_CUDA(cudaMemcpyAsync(o->boards + 16 * lo, e->d_boards + 16 * lo, 16 * m, cudaMemcpyDeviceToHost, s));
+    G2048_CUDA(cudaMemcpyAsync(o->rewards + lo, e->d_rewards + lo, 4 * m, cudaMemcpyDeviceToHost, s));
+    G2048_CUDA(cudaMemcpyAsync(o->dones + lo, e->d_dones + lo, m, cudaMemcpyDeviceToHost, s));
+    if (o->illegal) G2048_CUDA(cudaMemcpyAsync(o->illegal + lo, e->d_illegal + lo, m, cudaMemcpyDeviceToHost, s));
+    if (o->highest_exp) G2048_CUDA(cudaMemcpyAsync(o->highest_exp + lo, e->d_highest + lo, m, cudaMemcpyDeviceToHost, s));
+    if (o->legal_mask) G2048_CUDA(cudaMemcpyAsync(o->legal_mask + lo, e->d_mask + lo, m, cudaMemcpyDeviceToHost, s));
+  }
+  e->step_index += 1;
+  return env_sync(e);
+}
+
+int g2048_env_device_ptrs(G2048Env* e, uint8_t** boards, float** rewards, uint8_t** dones) {
+  if (!e) return fail(G2048_ERR_INVALID, "g2048_env_device_ptrs: env is NULL");
+  if (boards) *boards = e->d_boards;
+  if (rewards) *rewards = e->d_rewards;
+  if (dones) *dones = e->d_dones;
+  return G2048_OK;
+}
+
+uint64_t g2048_env_step_index(const G2048Env* e) { return e ? e->step_index : 0; }
+
+}  // extern "C"

@@ -87,6 +87,10 @@ typedef struct G2048StepArgs {
   uint32_t*       final_len;       /* [n]    out, nullable: episode length, where done     */
   const uint32_t* forced_draws;    /* [n*4]  nullable: words used INSTEAD of the Philox    */
                                    /*        output w[0..3] (fixture / CSV parity)         */
+  uint64_t*       step_counter;    /* nullable device uint64: when set the step index is   */
+                                   /*        read from *step_counter instead of step_index */
+                                   /*        and a follow-up kernel on the same stream     */
+                                   /*        increments it (CUDA-graph capture friendly)   */
   uint64_t        n;               /* boards in this call                                  */
   uint64_t        env_id_base;     /* global env id of element 0                           */
   uint64_t        seed;            /* Philox key                                           */
@@ -108,6 +112,14 @@ int g2048_step(const G2048StepArgs* args, void* stream);
 int g2048_reset(uint8_t* boards, const uint8_t* reset_mask, uint64_t n,
                 uint64_t env_id_base, uint64_t seed, uint64_t reset_index,
                 void* stream);
+
+/*
+ * Game2048Env.add_tile (game2048_env.py:166-176) on its own: one spawn per board with the
+ * step-tag draw word w[0] at `step_index` (boards without an empty cell are left alone,
+ * where the reference asserts, :176).
+ */
+int g2048_add_tile(uint8_t* boards, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                   uint64_t step_index, void* stream);
 
 /*
  * Game2048Env.move(direction, trial) (game2048_env.py:194-241) without spawn:

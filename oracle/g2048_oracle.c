@@ -158,7 +158,7 @@ static void step_one(const G2048StepArgs* a, uint64_t i) {
   int action = a->actions[i] & 3;
   uint32_t w[4];
   if (a->forced_draws) memcpy(w, a->forced_draws + 4 * i, sizeof w);
-  else draw_words(a->seed, a->env_id_base + i, a->step_index, 0, w);
+  else draw_words(a->seed, a->env_id_base + i, a->step_counter ? *a->step_counter : a->step_index, 0, w);
 
   uint32_t score = 0;
   float reward;
@@ -198,6 +198,7 @@ static void step_one(const G2048StepArgs* a, uint64_t i) {
 int g2048_oracle_step(const G2048StepArgs* a) {
   if (!a || !a->boards || !a->actions || !a->rewards || !a->dones) return G2048_ERR_INVALID;
   for (uint64_t i = 0; i < a->n; ++i) step_one(a, i);
+  if (a->step_counter) *a->step_counter += 1;
   return G2048_OK;
 }
 
@@ -225,6 +226,7 @@ int g2048_oracle_step_mt(const G2048StepArgs* a, int threads) {
   }
   for (int t = 0; t < started; ++t) pthread_join(tid[t], 0);
   for (int t = started; t < threads; ++t) step_slice(&sl[t]);
+  if (a->step_counter) *a->step_counter += 1;
   return G2048_OK;
 }
 
@@ -236,6 +238,17 @@ int g2048_oracle_reset(uint8_t* boards, const uint8_t* reset_mask, uint64_t n,
     uint32_t w[4];
     draw_words(seed, env_id_base + i, reset_index, 1, w);
     reset_board(boards + 16 * i, w);
+  }
+  return G2048_OK;
+}
+
+int g2048_oracle_add_tile(uint8_t* boards, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                          uint64_t step_index) {
+  if (!boards) return G2048_ERR_INVALID;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t w[4];
+    draw_words(seed, env_id_base + i, step_index, 0, w);
+    spawn(boards + 16 * i, w[0]);
   }
   return G2048_OK;
 }

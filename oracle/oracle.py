@@ -18,7 +18,7 @@ class StepArgs(C.Structure):
         ("legal_mask", C.c_void_p), ("terminal_boards", C.c_void_p),
         ("ep_score", C.c_void_p), ("ep_len", C.c_void_p),
         ("final_score", C.c_void_p), ("final_len", C.c_void_p),
-        ("forced_draws", C.c_void_p),
+        ("forced_draws", C.c_void_p), ("step_counter", C.c_void_p),
         ("n", C.c_uint64), ("env_id_base", C.c_uint64), ("seed", C.c_uint64),
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
@@ -106,7 +106,7 @@ class OracleBatch:
         a = StepArgs(_p(self.boards), _p(actions), _p(out["rewards"]), _p(out["dones"]),
                      _p(out["illegal"]), _p(out["highest_exp"]), _p(out["legal_mask"]),
                      _p(out["terminal_boards"]), _p(self.ep_score), _p(self.ep_len),
-                     _p(out["final_score"]), _p(out["final_len"]), _p(fd),
+                     _p(out["final_score"]), _p(out["final_len"]), _p(fd), None,
                      n, self.env_id_base, self.seed, self.step_index,
                      self.illegal_move_reward, self.max_tile_exp, self.flags)
         if self.threads > 1:
@@ -117,6 +117,14 @@ class OracleBatch:
         self.step_index += 1
         out["boards"] = self.boards
         return out
+
+
+def add_tile(boards, env_id_base, seed, step_index):
+    b = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 16).copy()
+    rc = lib().g2048_oracle_add_tile(_p(b), C.c_uint64(len(b)), C.c_uint64(env_id_base), C.c_uint64(seed),
+                                     C.c_uint64(step_index))
+    assert rc == 0
+    return b
 
 
 def move(boards, directions):

@@ -1,0 +1,113 @@
+// Host-side simulation of the CUDA step logic — TEST ONLY.
+//
+// Compiles gym-2048_b200/csrc/g2048_device.cuh with g++ (G2048_HOST_SIM: prmt/umulhi/popc
+// emulated) so the exact byte-SIMD code the kernel runs can be checked against the oracle
+// and the golden vectors on the GPU-less build box.  Never loaded by the product.
+#define G2048_HOST_SIM 1
+#include <cstring>
+#include "../../gym-2048_b200/csrc/g2048_device.cuh"
+#include "../../include/g2048.h"
+
+using namespace g2048;
+
+static inline void load(const uint8_t* b, uint32_t r[4]) { std::memcpy(r, b, 16); }
+static inline void store(uint8_t* b, const uint32_t r[4]) { std::memcpy(b, r, 16); }
+
+extern "C" int sim_step(const G2048StepArgs* p) {
+  for (uint64_t i = 0; i < p->n; ++i) {
+    uint32_t r[4];
+    load(p->boards + 16 * i, r);
+    Words w;
+    if (p->forced_draws) {
+      const uint32_t* f = p->forced_draws + 4 * i;
+      w = Words{f[0], f[1], f[2], f[3]};
+    } else {
+      w = draw_words(p->seed, p->env_id_base + i, p->step_counter ? *p->step_counter : p->step_index, 0);
+    }
+    const bool auto_reset = (p->flags & G2048_FLAG_AUTO_RESET) != 0;
+    StepOut o = step_board(r[0], r[1], r[2], r[3], p->actions[i] & 3u, w, p->max_tile_exp,
+                           p->highest_exp != nullptr, auto_reset);
+    store(p->boards + 16 * i, r);
+    p->rewards[i] = o.legal ? (float)o.score : p->illegal_move_reward;
+    p->dones[i] = o.done;
+    if (p->illegal) p->illegal[i] = !o.legal;
+    if (p->highest_exp) p->highest_exp[i] = (uint8_t)o.highest;
+    uint32_t es = p->ep_score ? p->ep_score[i] + o.score : 0, el = p->ep_len ? p->ep_len[i] + 1 : 0;
+    if (o.done) {
+      const uint32_t t[4] = {o.t0, o.t1, o.t2, o.t3};
+      if (p->terminal_boards) store(p->terminal_boards + 16 * i, t);
+      if (p->final_score) p->final_score[i] = es;
+      if (p->final_len) p->final_len[i] = el;
+      if (auto_reset) es = el = 0;
+    }
+    if (p->ep_score) p->ep_score[i] = es;
+    if (p->ep_len) p->ep_len[i] = el;
+    if (p->legal_mask) p->legal_mask[i] = (uint8_t)legal_mask(r[0], r[1], r[2], r[3]);
+  }
+  if (p->step_counter) *p->step_counter += 1;
+  return 0;
+}
+
+extern "C" int sim_reset(uint8_t* boards, const uint8_t* mask, uint64_t n, uint64_t base, uint64_t seed,
+                         uint64_t reset_index) {
+  for (uint64_t i = 0; i < n; ++i) {
+    if (mask && !mask[i]) continue;
+    Words w = draw_words(seed, base + i, reset_index, 1);
+    uint32_t r[4];
+    fresh_board(w.w1, w.w2, r[0], r[1], r[2], r[3]);
+    store(boards + 16 * i, r);
+  }
+  return 0;
+}
+
+extern "C" int sim_add_tile(uint8_t* boards, uint64_t n, uint64_t base, uint64_t seed, uint64_t step_index) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r[4];
+    load(boards + 16 * i, r);
+    Words w = draw_words(seed, base + i, step_index, 0);
+    spawn(r[0], r[1], r[2], r[3], w.w0);
+    store(boards + 16 * i, r);
+  }
+  return 0;
+}
+
+extern "C" int sim_move(const uint8_t* in, uint8_t* out, const uint8_t* dirs, uint32_t* scores,
+                        uint8_t* changed, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r[4], a, b, c, d;
+    load(in + 16 * i, r);
+    const uint32_t act = dirs[i] & 3u;
+    orient(kOrientIn[act], r[0], r[1], r[2], r[3], a, b, c, d);
+    const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
+    const uint32_t s = slide_merge(a, b, c, d);
+    orient(kOrientOut[act], a, b, c, d, r[0], r[1], r[2], r[3]);
+    if (out) store(out + 16 * i, r);
+    if (scores) scores[i] = s;
+    if (changed) changed[i] = ((a ^ a0) | (b ^ b0) | (c ^ c0) | (d ^ d0)) != 0;
+  }
+  return 0;
+}
+
+extern "C" int sim_status(const uint8_t* boards, uint8_t* lm, uint8_t* hi, uint8_t* ne, uint8_t* end,
+                          uint32_t max_tile_exp, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r[4];
+    load(boards + 16 * i, r);
+    const uint32_t empties = count_empty(r[0], r[1], r[2], r[3]);
+    const uint32_t h = highest_exp(r[0], r[1], r[2], r[3]);
+    if (lm) lm[i] = (uint8_t)legal_mask(r[0], r[1], r[2], r[3]);
+    if (hi) hi[i] = (uint8_t)h;
+    if (ne) ne[i] = (uint8_t)empties;
+    if (end) end[i] = (max_tile_exp != 0 && h == max_tile_exp) ||
+                      (empties == 0 && full_board_is_dead(r[0], r[1], r[2], r[3]));
+  }
+  return 0;
+}
+
+extern "C" int sim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    Words w = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+    out[4 * i] = w.w0; out[4 * i + 1] = w.w1; out[4 * i + 2] = w.w2; out[4 * i + 3] = w.w3;
+  }
+  return 0;
+}

@@ -1,0 +1,84 @@
+"""CPU-only checks of the boundary: the C-ABI library builds, loads and exports every symbol
+include/g2048.h declares (no compute calls without a GPU), struct layouts match the header,
+host helpers behave, and the product never imports the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import gym_2048_b200 as g
+from conftest import ROOT
+from oracle import oracle
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "g2048.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(g2048_\w+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    g.build()
+    L = g._lib.lib()
+    names = header_functions()
+    assert len(names) >= 17
+    for name in names:
+        assert hasattr(L, name), name
+    assert sorted(g._lib.EXPORTS) == names
+    assert L.g2048_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    """sizeof/offsetof of the ctypes mirrors == what gcc computes from include/g2048.h."""
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "g2048.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(G2048StepArgs), offsetof(G2048StepArgs, n),
+             offsetof(G2048StepArgs, illegal_move_reward), offsetof(G2048StepArgs, flags),
+             sizeof(G2048EnvConfig), sizeof(G2048HostStepOut));
+      return 0;
+    }'''
+    d = os.path.join(ROOT, "tests", "host_sim")
+    src, exe = os.path.join(d, "_layout.c"), os.path.join(d, "_layout.bin")
+    open(src, "w").write(prog)
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+    out = [int(x) for x in subprocess.check_output([exe]).split()]
+    os.remove(src), os.remove(exe)
+    for S in (g._lib.StepArgs, oracle.StepArgs):
+        assert [C.sizeof(S), S.n.offset, S.illegal_move_reward.offset, S.flags.offset] == out[:4]
+    assert C.sizeof(g._lib.EnvConfig) == out[4] and C.sizeof(g._lib.HostStepOut) == out[5]
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(g.G2048Error):
+        g.BatchedGame2048(8)
+    with pytest.raises(g.G2048Error):
+        g.Game2048Env().reset(seed=0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym-2048_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU", ""), os.path.join(dirpath, f)
+
+
+def test_tile_to_exp_and_shard_range():
+    assert g.tile_to_exp(None) == 0 and g.tile_to_exp(2048) == 11 and g.tile_to_exp(2) == 1
+    assert g.tile_to_exp(3000) == 63 and g.tile_to_exp(0) == 63 and g.tile_to_exp(1) == 63
+    with pytest.raises(AssertionError):
+        g.tile_to_exp(2048.0)                      # reference :72 asserts int
+    for total, world in ((1 << 20, 8), (10, 3), (7, 8)):
+        spans = [g.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (b0, c0), (b1, _) in zip(spans, spans[1:]):
+            assert b0 + c0 == b1

@@ -1,0 +1,259 @@
+"""The single-env class, observations, VecEnv adapter and host-buffer handle on the GPU.
+
+TestBoard / TestStep restate the reference's env/envs/test_game2048_env.py known answers
+(file:line in comments) against gym_2048_b200.Game2048Env, so a user of the reference class
+finds the same behaviour."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+MOVE_BOARD = [[0, 2, 0, 4], [2, 2, 8, 0], [2, 2, 2, 8], [2, 2, 4, 4]]
+DEAD = [[2, 4, 8, 16], [4, 8, 16, 2], [8, 16, 2, 4], [16, 2, 4, 8]]
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gym_2048_b200
+    return gym_2048_b200
+
+
+class TestBoard:
+    def test_shift(self, g):                                     # test_game2048_env.py:10-34
+        b = g.Game2048Env()
+        assert b.shift([0, 0, 0, 0]) == ([0, 0, 0, 0], 0)
+        assert b.shift([0, 2, 0, 0]) == ([2, 0, 0, 0], 0)
+        assert b.shift([0, 2, 0, 4]) == ([2, 4, 0, 0], 0)
+        assert b.shift([2, 4, 8, 16]) == ([2, 4, 8, 16], 0)
+        assert b.shift([2, 2, 8, 0]) == ([4, 8, 0, 0], 4)
+        assert b.shift([4, 2, 2, 4]) == ([4, 4, 4, 0], 4)
+        assert b.shift([2, 2, 2, 8]) == ([4, 2, 8, 0], 4)
+        assert b.shift([2, 8, 4, 4]) == ([2, 8, 8, 0], 8)
+        assert b.shift([2, 2, 4, 4]) == ([4, 8, 0, 0], 12)
+        assert b.shift([2, 4, 4, 4]) == ([2, 8, 4, 0], 8)
+        assert b.shift([4, 4, 4, 4]) == ([8, 8, 0, 0], 16)
+        assert b.shift([0, 2, 2, 8]) == ([4, 8, 0, 0], 4)
+
+    def test_move(self, g):                                      # :36-98
+        b = g.Game2048Env()
+        want = {0: ([[4, 4, 8, 4], [2, 4, 2, 8], [0, 0, 4, 4], [0, 0, 0, 0]], 12),
+                1: ([[0, 0, 2, 4], [0, 0, 4, 8], [0, 2, 4, 8], [0, 0, 4, 8]], 20),
+                2: ([[0, 0, 0, 0], [0, 0, 8, 4], [2, 4, 2, 8], [4, 4, 4, 4]], 12),
+                3: ([[2, 4, 0, 0], [4, 8, 0, 0], [4, 2, 8, 0], [4, 8, 0, 0]], 20)}
+        for d in (0, 1, 2, 3):
+            b.set_board(np.array(MOVE_BOARD))
+            assert b.move(d) == want[d][1]
+            assert np.array_equal(b.get_board(), np.array(want[d][0]))
+        with pytest.raises(g.IllegalMove):                       # :89-90
+            b.move(3)
+        assert b.move(2) == 8                                    # :93-98
+        assert np.array_equal(b.get_board(), np.array([[0, 4, 0, 0], [2, 8, 0, 0], [4, 2, 0, 0], [8, 8, 8, 0]]))
+
+    def test_trial_move_leaves_board(self, g):
+        b = g.Game2048Env()
+        b.set_board(np.array(MOVE_BOARD))
+        assert b.move(0, trial=True) == 12
+        assert np.array_equal(b.get_board(), np.array(MOVE_BOARD))
+
+    def test_set_board_aliases_callers_array(self, g):
+        b = g.Game2048Env()
+        arr = np.array(MOVE_BOARD)
+        b.set_board(arr)
+        b.move(0)
+        assert b.get_board() is arr and arr[0, 0] == 4
+
+    def test_highest(self, g):                                   # :100-107
+        b = g.Game2048Env()
+        b.set_board(np.array([[0, 2, 0, 4], [2, 2, 8, 0], [2, 2, 2048, 8], [2, 2, 4, 4]]))
+        assert b.highest() == 2048
+
+    def test_isend(self, g):                                     # :109-151
+        b = g.Game2048Env()
+        b.set_board(np.array([[2] * 4] * 4))
+        assert b.isend() == False                                # noqa: E712
+        b.set_board(np.array(DEAD))
+        assert b.isend() == True                                 # noqa: E712
+        hole = np.array(DEAD)
+        hole[3, 3] = 0
+        b.set_board(hole)
+        assert b.isend() == False                                # noqa: E712
+        b.set_max_tile(2048)
+        lone = np.zeros((4, 4), int)
+        lone[0, 0] = 2048
+        b.set_board(lone)
+        assert b.isend() == True                                 # noqa: E712
+        lone[0, 0] = 1024
+        b.set_board(lone)
+        assert b.isend() == False                                # noqa: E712
+
+
+class TestStep:
+    def test_step_returns_correct_shapes(self, g):               # :154-163
+        b = g.Game2048Env()
+        b.reset(seed=0)
+        obs, reward, terminated, truncated, info = b.step(0)
+        assert obs.shape == (16, 4, 4)
+        assert isinstance(reward, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+        assert 'illegal_move' in info and 'highest' in info
+
+    def test_step_reward_and_score(self, g):                     # :165-192
+        b = g.Game2048Env()
+        b.reset(seed=0)
+        b.set_board(np.array([[0] * 4, [0] * 4, [2, 0, 0, 0], [2, 0, 0, 0]]))
+        assert b.step(0)[1] == 4.0
+        b.set_board(np.array([[0] * 4, [0] * 4, [4, 0, 0, 0], [4, 0, 0, 0]]))
+        b.step(0)
+        assert b.score == 12.0
+
+    def test_step_illegal_move(self, g):                         # :194-217
+        b = g.Game2048Env()
+        b.reset(seed=0)
+        b.set_board(np.array(DEAD))
+        obs, reward, terminated, truncated, info = b.step(0)
+        assert terminated == True and info['illegal_move'] == True and reward == 0.0   # noqa: E712
+        assert np.array_equal(b.get_board(), np.array(DEAD))
+        b = g.Game2048Env()
+        b.set_illegal_move_reward(-1.0)
+        b.reset(seed=0)
+        b.set_board(np.array(DEAD))
+        assert b.step(0)[1] == -1.0
+
+    def test_step_observation_is_valid_one_hot(self, g):         # :219-231
+        b = g.Game2048Env()
+        b.reset(seed=0)
+        b.set_board(np.array([[2, 0, 0, 0], [0] * 4, [0] * 4, [0, 0, 4, 0]]))
+        obs = b.step(1)[0]
+        assert obs.shape == (16, 4, 4) and obs.sum(axis=0).max() <= 1
+        assert set(obs.flatten().tolist()) == {0, 1}
+        assert obs.dtype == np.int64
+
+    def test_reset_is_seed_deterministic_and_matches_oracle(self, g):
+        a, b = g.Game2048Env(), g.Game2048Env()
+        oa, _ = a.reset(seed=456)
+        ob, _ = b.reset(seed=456)
+        assert np.array_equal(oa, ob) and (a.get_board() != 0).sum() == 2 and a.score == 0
+        o = oracle.OracleBatch(1, seed=456, auto_reset=False)
+        assert np.array_equal(oracle.exp_to_values(o.reset()[0]).reshape(4, 4), a.get_board())
+        rng = np.random.default_rng(0)
+        for _ in range(60):                                      # same game as the oracle, step by step
+            act = int(rng.integers(4))
+            out = o.step([act])
+            obs, reward, terminated, _, info = a.step(act)
+            assert np.array_equal(oracle.exp_to_values(o.boards[0]).reshape(4, 4), a.get_board())
+            assert reward == out["rewards"][0] and terminated == bool(out["dones"][0])
+            assert info["illegal_move"] == bool(out["illegal"][0])
+            assert info["highest"] == (1 << int(out["highest_exp"][0]))
+            if terminated:
+                break
+
+    def test_stack_function(self, g):                            # reference stack :17-32
+        z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "special.npz"))
+        for i in (0, 3, 7, 8, 9):
+            vals = oracle.exp_to_values(z["boards"][i]).reshape(4, 4)
+            assert np.array_equal(g.stack(vals), z["obs"][i].astype(int))
+
+
+def test_observe_all_dtypes_match_reference_stack(g):
+    import torch
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "special.npz"))
+    boards = z["boards"]
+    game = g.BatchedGame2048(len(boards), outputs=())
+    game.set_boards(torch.from_numpy(boards))
+    for dt in (torch.uint8, torch.float32, torch.int64, torch.bfloat16):
+        obs = game.observe(dt)
+        assert obs.dtype == dt and tuple(obs.shape) == (len(boards), 16, 4, 4)
+        assert np.array_equal(obs.float().cpu().numpy().astype(np.uint8), z["obs"])
+    vals = game.board_values().cpu().numpy().reshape(-1, 16)
+    assert np.array_equal(vals, oracle.exp_to_values(boards))
+    game2 = g.BatchedGame2048(len(boards), outputs=())
+    game2.set_board_values(torch.from_numpy(vals))
+    assert torch.equal(game2.boards, game.boards)
+    with pytest.raises(ValueError):
+        game2.set_board_values(torch.full((len(boards), 16), 3))
+
+
+def test_vec_env_sb3_semantics(g):
+    n = 512
+    venv = g.Game2048VecEnv(n, seed=7, obs_dtype=__import__("torch").uint8)
+    o = oracle.OracleBatch(n, seed=7)
+    obs = venv.reset()
+    assert obs.shape == (n, 16, 4, 4) and np.array_equal(obs, oracle.encode_obs_u8(o.reset()))
+    assert venv.observation_space.shape == (16, 4, 4) and venv.action_space.n == 4
+    rng = np.random.default_rng(3)
+    n_done = 0
+    for t in range(60):
+        act = rng.integers(0, 4, n)
+        venv.step_async(act)
+        obs, rew, dones, infos = venv.step_wait()
+        out = o.step(act.astype(np.uint8))
+        assert rew.dtype == np.float32 and dones.dtype == np.bool_ and len(infos) == n
+        assert np.array_equal(obs, oracle.encode_obs_u8(o.boards))
+        assert np.array_equal(rew, out["rewards"]) and np.array_equal(dones, out["dones"] != 0)
+        for i in np.flatnonzero(dones):
+            info = infos[i]
+            assert info["TimeLimit.truncated"] is False
+            assert np.array_equal(info["terminal_observation"], oracle.encode_obs_u8(out["terminal_boards"][i])[0])
+            assert info["episode"]["r"] == float(out["final_score"][i]) and info["episode"]["l"] == int(out["final_len"][i])
+            assert info["highest"] == (1 << int(out["highest_exp"][i])) and info["illegal_move"] == bool(out["illegal"][i])
+            n_done += 1
+        masks = venv.action_masks()
+        assert np.array_equal(masks, ((out["legal_mask"][:, None] >> np.arange(4)) & 1).astype(bool))
+    assert n_done > 50
+
+
+def test_host_stepped_env_matches_oracle(g):
+    n = 20000
+    h = g.HostSteppedEnv(n, seed=9, n_chunks=3, extras=True)
+    o = oracle.OracleBatch(n, seed=9, threads=4)
+    assert np.array_equal(h.reset().numpy(), o.reset())
+    rng = np.random.default_rng(1)
+    for t in range(30):
+        act = rng.integers(0, 4, n).astype(np.uint8)
+        b = h.step(act)
+        out = o.step(act)
+        assert np.array_equal(b.boards.numpy(), o.boards)
+        assert np.array_equal(b.rewards.numpy(), out["rewards"]) and np.array_equal(b.dones.numpy(), out["dones"])
+        assert np.array_equal(b.illegal.numpy(), out["illegal"])
+        assert np.array_equal(b.highest_exp.numpy(), out["highest_exp"])
+        assert np.array_equal(b.legal_mask.numpy(), out["legal_mask"])
+    assert h.step_index == 30
+    h.close()
+
+
+def test_checkpoint_resume_is_exact(g):
+    import torch
+    n = 4096
+    a = g.BatchedGame2048(n, seed=5)
+    a.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    acts = [torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.uint8) for _ in range(40)]
+    for t in range(20):
+        a.step(acts[t])
+    sd = a.state_dict()
+    b = g.BatchedGame2048(n, seed=999)
+    b.load_state_dict(sd)
+    for t in range(20, 40):
+        ra, rb = a.step(acts[t]), b.step(acts[t])
+        assert torch.equal(ra.boards, rb.boards) and torch.equal(ra.rewards, rb.rewards)
+        assert torch.equal(a.ep_score, b.ep_score)
+
+
+def test_argument_validation(g):
+    import ctypes as C
+    import torch
+    game = g.BatchedGame2048(64)
+    game.reset()
+    with pytest.raises(ValueError):
+        game.step(torch.full((64,), 4))
+    with pytest.raises(ValueError):
+        game.step(torch.zeros(63, dtype=torch.uint8))
+    L = g._lib.lib()
+    assert L.g2048_step(None, None) == -1 and b"NULL" in L.g2048_last_error()
+    a = g._lib.StepArgs()
+    a.n = 4
+    assert L.g2048_step(C.byref(a), None) == -1
+    buf = torch.zeros(4 * 16 + 1, dtype=torch.uint8, device="cuda")
+    assert L.g2048_reset(C.c_void_p(buf.data_ptr() + 1), None, 4, 0, 0, 0, None) == -2
+    assert L.g2048_encode_obs(C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr()), 99, 1, None) == -1

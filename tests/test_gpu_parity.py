@@ -1,0 +1,156 @@
+"""GPU parity tests proper: the product (libg2048.so through its C ABI, driven by
+gym_2048_b200.BatchedGame2048) against the golden vectors produced by the unmodified
+reference and against the pinned C oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from backends import GpuOps
+    return GpuOps
+
+
+def test_philox_on_device(ops):
+    pc.check_philox(ops)
+
+
+def test_shift_table_all_directions(ops):
+    pc.check_shift_table_all_directions(ops)
+
+
+def test_csv_transitions(ops):
+    pc.check_csv_transitions(ops)
+
+
+def test_special_boards(ops):
+    pc.check_special_boards(ops)
+
+
+def test_golden_rollouts(ops, golden_rollouts):
+    pc.check_rollouts(ops, golden_rollouts)
+
+
+def test_status_and_move_random_boards(ops):
+    pc.check_status_random_boards(ops)
+
+
+def test_add_tile(ops):
+    pc.check_add_tile(ops)
+
+
+def test_config2_65536_envs_fixture_seeds(ops):
+    """BASELINE config 2: 65,536 envs, random actions, bit-exact vs CPU on the fixture seeds."""
+    for seed in (0, 1, 42, 456):
+        pc.check_against_oracle(ops, n=65536, steps=24, seed=seed, policy="random", threads=8)
+
+
+def test_config2_long_random_rollout(ops):
+    pc.check_against_oracle(ops, n=65536, steps=256, seed=0, policy="random", threads=8)
+
+
+def test_config4_legal_mask_autoreset_midgame(ops):
+    """BASELINE config 4 flavour: legal-mask output + auto-reset, random-legal play (mid-game boards)."""
+    pc.check_against_oracle(ops, n=16384, steps=600, seed=42, policy="legal", illegal_move_reward=-1.0,
+                            env_id_base=(1 << 40) + 3, threads=8)
+
+
+def test_max_tile_and_no_autoreset(ops):
+    pc.check_against_oracle(ops, n=8192, steps=300, seed=456, policy="legal", max_tile_exp=6, auto_reset=False,
+                            threads=8)
+    pc.check_against_oracle(ops, n=8192, steps=300, seed=1, policy="legal", max_tile_exp=7, auto_reset=True,
+                            threads=8)
+
+
+def test_ragged_and_tiny_batches(ops):
+    for n in (1, 2, 31, 33, 255, 257, 1000):
+        pc.check_against_oracle(ops, n=n, steps=40, seed=n, policy="random", threads=1)
+
+
+def test_sharding_invariance_on_device(ops):
+    """Slices with env_id_base offsets reproduce the unsharded batch (no collective on the path)."""
+    import torch
+    import gym_2048_b200 as g
+    n, steps = 8192, 50
+    rng = np.random.default_rng(9)
+    acts = rng.integers(0, 4, (steps, n)).astype(np.uint8)
+    full = g.BatchedGame2048(n, seed=11, env_id_base=100, outputs=())
+    parts = [g.BatchedGame2048(c, seed=11, env_id_base=100 + b, outputs=())
+             for b, c in (g.shard_range(n, r, 3) for r in range(3))]
+    full.reset()
+    for p in parts:
+        p.reset()
+    for t in range(steps):
+        a = torch.from_numpy(acts[t]).cuda()
+        rf = full.step(a)
+        lo = 0
+        for p in parts:
+            rp = p.step(a[lo:lo + p.num_envs].contiguous())
+            assert torch.equal(rp.boards, rf.boards[lo:lo + p.num_envs])
+            assert torch.equal(rp.rewards, rf.rewards[lo:lo + p.num_envs])
+            assert torch.equal(rp.dones, rf.dones[lo:lo + p.num_envs])
+            lo += p.num_envs
+
+
+def test_lean_kernel_equals_full_kernel(ops):
+    """outputs=() runs the lean kernel variant; state, rewards and dones must not differ."""
+    import torch
+    import gym_2048_b200 as g
+    n = 50000
+    a = g.BatchedGame2048(n, seed=3, outputs=())
+    b = g.BatchedGame2048(n, seed=3)
+    a.reset(), b.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(100):
+        act = torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.uint8)
+        ra, rb = a.step(act), b.step(act)
+        assert torch.equal(ra.boards, rb.boards) and torch.equal(ra.rewards, rb.rewards)
+        assert torch.equal(ra.dones, rb.dones)
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 3 size (1,048,576 envs): size-independent properties + a sampled oracle check."""
+    import torch
+    import gym_2048_b200 as g
+    n = 1 << 20
+    game = g.BatchedGame2048(n, seed=42)
+    game.reset()
+    b0 = game.boards.clone()
+    assert int((b0 != 0).sum()) == 2 * n                      # two tiles per fresh board (:108-109)
+    assert int(b0.max()) <= 2
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sample = torch.randint(0, n, (4096,), generator=gen, device="cuda")
+    for t in range(20):
+        before = game.boards.clone()
+        tiles_before = game.board_values().sum(dim=(1, 2))
+        act = torch.randint(0, 4, (n,), generator=gen, device="cuda", dtype=torch.uint8)
+        r = game.step(act)
+        legal = ~r.illegal
+        # an illegal move leaves the terminal board untouched and pays the illegal reward
+        assert torch.equal(r.terminal_boards[r.illegal], before[r.illegal])
+        assert bool((r.rewards[r.illegal] == 0).all())
+        # tile-value conservation: a legal move adds exactly the spawned 2 or 4
+        post = torch.where(r.dones[:, None], r.terminal_boards, r.boards)
+        grow = game.board_values(post.contiguous()).sum(dim=(1, 2)) - tiles_before
+        assert bool(((grow[legal] == 2) | (grow[legal] == 4)).all()) and bool((grow[r.illegal] == 0).all())
+        # every reset board has exactly two tiles
+        assert bool(((r.boards[r.dones] != 0).sum(dim=1) == 2).all())
+        # sampled envs against the oracle on the same boards/actions/draws
+        idx = sample.cpu().numpy()
+        ob = oracle.OracleBatch(1, seed=42)
+        for i in idx[:256]:
+            ob.boards[0] = before[i].cpu().numpy()
+            ob.env_id_base, ob.step_index = int(i), t
+            o = ob.step(np.array([int(act[i])], dtype=np.uint8))
+            assert np.array_equal(ob.boards[0], r.boards[i].cpu().numpy())
+            assert o["rewards"][0] == float(r.rewards[i]) and o["dones"][0] == int(r.dones[i])
+    # mean P(4) over spawns ~ 0.1
+    fours = (b0 == 2).sum().item() / (2 * n)
+    assert abs(fours - 0.1) < 0.002
