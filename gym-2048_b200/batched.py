@@ -309,6 +309,7 @@ class HostSteppedEnv:
         cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
                              int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
                              int(n_chunks), 0)
+        self._n_chunks = min(int(n_chunks) if n_chunks else 4, 64)
         self._h = C.c_void_p()
         check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
         self.buffers = HostBuffers(self.num_envs, extras)
@@ -328,6 +329,22 @@ class HostSteppedEnv:
         check(self.lib.g2048_env_step_host(self._h, C.c_void_p(self.buffers.actions.data_ptr()),
                                            C.byref(self._out)))
         return self.buffers
+
+    def step_pinned(self, actions):
+        """Like step(), reading the actions straight from the caller's (ideally pinned) host
+        tensor instead of staging them through buffers.actions."""
+        if actions.dtype != torch.uint8 or actions.numel() != self.num_envs or actions.is_cuda \
+                or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous host uint8 tensor with one entry per env")
+        check(self.lib.g2048_env_step_host(self._h, C.c_void_p(actions.data_ptr()), C.byref(self._out)))
+        return self.buffers
+
+    @property
+    def n_chunks_effective(self):
+        """Kernel launches per step_host call (the library rounds slices up to 256 boards)."""
+        per = -(-self.num_envs // self._n_chunks)
+        per = -(-per // 256) * 256
+        return -(-self.num_envs // per)
 
     @property
     def step_index(self):
