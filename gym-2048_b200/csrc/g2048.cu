@@ -79,6 +79,7 @@ struct StepParams {
   const uint4* forced_draws;
   const uint64_t* step_counter;
   uint64_t n, env_id_base, seed, step_index;
+  RoundKeys rk;                 // Philox round keys of `seed`
   float illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t flags;
@@ -86,12 +87,21 @@ struct StepParams {
 
 // Game2048Env.step (:76-100) for n boards.  EXTRAS=false is the lean variant used when
 // none of the optional outputs/inputs is requested (boards, actions, rewards, dones only).
+// The 32 one-tile boards fresh_board() ORs together, built once per CTA in shared memory.
+__device__ __forceinline__ const Board4* make_reset_lut(Board4* s_lut) {
+  if (threadIdx.x < 32) s_lut[threadIdx.x] = one_tile_board(threadIdx.x);
+  __syncthreads();
+  return s_lut;
+}
+
 template <bool EXTRAS>
 __global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p) {
+  __shared__ Board4 s_lut[32];
+  const Board4* lut = make_reset_lut(s_lut);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
-  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  const uint32_t n = (uint32_t)p.n, stride = gridDim.x * kThreads;     // n < 2^32 (checked by the host)
   const uint64_t step_index = p.step_counter ? *p.step_counter : p.step_index;
-  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += stride) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     uint4 bd = p.boards[i];
     const uint32_t action = p.actions[i] & 3u;
     Words w;
@@ -99,18 +109,20 @@ __global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p
       const uint4 f = p.forced_draws[i];
       w = Words{f.x, f.y, f.z, f.w};
     } else {
-      w = draw_words(p.seed, p.env_id_base + i, step_index, 0u);
+      const uint64_t env = p.env_id_base + i;
+      w = philox4x32_10_rk((uint32_t)step_index, (uint32_t)(step_index >> 32), (uint32_t)env,
+                           (uint32_t)(env >> 32) & 0x7FFFFFFFu, p.rk);
     }
-    const StepOut o = step_board(bd.x, bd.y, bd.z, bd.w, action, w, p.max_tile_exp,
+    const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action, w, p.max_tile_exp,
                                  EXTRAS && p.highest_exp != nullptr, auto_reset);
     p.boards[i] = bd;
-    p.rewards[i] = o.legal ? (float)o.score : p.illegal_move_reward;   // :90 / :95
+    p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
     p.dones[i] = o.done ? 1 : 0;
     if (EXTRAS) {
       if (p.illegal) p.illegal[i] = o.legal ? 0 : 1;                   // :82, :93
       if (p.highest_exp) p.highest_exp[i] = (uint8_t)o.highest;        // :97
       uint32_t es = 0, el = 0;
-      if (p.ep_score) es = p.ep_score[i] + o.score;                    // :86
+      if (p.ep_score) es = p.ep_score[i] + (uint32_t)o.score;          // :86
       if (p.ep_len) el = p.ep_len[i] + 1u;
       if (o.done) {
         if (p.terminal_boards) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
@@ -131,12 +143,14 @@ __global__ void g2048_bump_counter_kernel(uint64_t* counter) { *counter += 1ull;
 __global__ void __launch_bounds__(kThreads)
 g2048_reset_kernel(uint4* boards, const uint8_t* reset_mask, uint64_t n, uint64_t env_id_base, uint64_t seed,
                    uint64_t reset_index) {
+  __shared__ Board4 s_lut[32];
+  const Board4* lut = make_reset_lut(s_lut);
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
   for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     if (reset_mask && !reset_mask[i]) continue;
     const Words w = draw_words(seed, env_id_base + i, reset_index, 1u);
     uint4 bd;
-    fresh_board(w.w1, w.w2, bd.x, bd.y, bd.z, bd.w);
+    fresh_board(lut, w.w1, w.w2, bd.x, bd.y, bd.z, bd.w);
     boards[i] = bd;
   }
 }
@@ -164,7 +178,7 @@ g2048_move_kernel(const uint4* in, uint4* out, const uint8_t* directions, uint32
     uint32_t a, b, c, d;
     orient(kOrientIn[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
     const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
-    const uint32_t s = slide_merge(a, b, c, d);
+    const uint32_t s = (uint32_t)slide_merge(a, b, c, d);
     orient(kOrientOut[act], a, b, c, d, bd.x, bd.y, bd.z, bd.w);
     if (out) out[i] = bd;
     if (scores) scores[i] = s;
@@ -314,6 +328,7 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   if (!aligned16(a->boards) || !aligned16(a->terminal_boards) || !aligned16(a->forced_draws))
     return fail(G2048_ERR_ALIGN, "g2048_step: boards / terminal_boards / forced_draws must be 16-byte aligned");
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
+  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
   StepParams p;
   p.boards = reinterpret_cast<uint4*>(a->boards);
   p.actions = a->actions;
@@ -332,6 +347,7 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   p.n = a->n;
   p.env_id_base = a->env_id_base;
   p.seed = a->seed;
+  make_round_keys(a->seed, p.rk);
   p.step_index = a->step_index;
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;

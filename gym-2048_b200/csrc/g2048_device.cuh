@@ -53,10 +53,28 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 #endif
+// Pipe balancing.  The step is bound by the integer ALU pipe (LOP3/PRMT/SHF/IADD3 issue at
+// half rate); the FMA pipe, where IMAD runs, is mostly idle.  addf() is an add that ptxas
+// must keep as IMAD (x * one + y with `one` read from constant memory, so it cannot be
+// strength-reduced back to IADD3), shr() a right shift done as IMAD.HI.
+#ifdef G2048_HOST_SIM
+inline uint32_t addf(uint32_t x, uint32_t y) { return x + y; }
+template <int S> inline uint32_t shr(uint32_t x) { return x >> S; }
+template <int S> inline uint32_t shl(uint32_t x) { return x << S; }
+#else
+__constant__ uint32_t kOne = 1u;
+__device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(kOne), "r"(y));
+  return d;
+}
+template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
+template <int S> __device__ __forceinline__ uint32_t shl(uint32_t x) { return x * (1u << S); }
+#endif
 // 0xFF in every byte whose bit 7 is set, else 0x00.
 G2048_DEV uint32_t spread(uint32_t x) { return prmt(x, 0u, 0xBA98u); }
 // 0xFF where the byte of x is non-zero (bytes of x <= 0x80).
-G2048_DEV uint32_t nzmask(uint32_t x) { return spread(x + L7); }
+G2048_DEV uint32_t nzmask(uint32_t x) { return spread(addf(x, L7)); }
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) ------------------------------------------
 struct Words { uint32_t w0, w1, w2, w3; };
@@ -75,6 +93,29 @@ G2048_DEV Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     k1 += 0xBB67AE85u;
   }
   return Words{c0, c1, c2, c3};
+}
+
+// Same with the 10 round keys precomputed (host side, passed in kernel-parameter constant
+// memory): the key schedule then costs no instruction at all in the hot loop.
+struct RoundKeys { uint32_t k0[10], k1[10]; };
+G2048_DEV Words philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk.k0[r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ rk.k1[r];
+    c3 = lo0;
+  }
+  return Words{c0, c1, c2, c3};
+}
+inline void make_round_keys(uint64_t seed, RoundKeys& rk) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    rk.k0[r] = k0; rk.k1[r] = k1;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
 }
 
 // Draw words for (seed, global env id, index, tag) — include/g2048.h "Draw stream".
@@ -127,40 +168,51 @@ G2048_DEV void bubble(uint32_t& x, uint32_t& y) {
   y &= m;
 }
 
-// Slide (a,b,c,d) toward a with merging; returns the move score (:254).
-G2048_DEV uint32_t slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+// 2^e (e = byte k of the biased slot word, 0 where the slot is empty) as a float: the byte is
+// e+127, moved onto the exponent field (bits 23..30); an empty slot gives +0.0f.
+template <int K> G2048_DEV float slot_pow2(uint32_t biased) {
+  constexpr uint32_t EXPF = 0x7F800000u;
+  uint32_t bits;
+  if (K == 3) bits = (biased >> 1) & EXPF;
+  else bits = shl<23 - 8 * K>(biased) & EXPF;
+#ifdef G2048_HOST_SIM
+  float f;
+  __builtin_memcpy(&f, &bits, 4);
+  return f;
+#else
+  return __uint_as_float(bits);
+#endif
+}
+G2048_DEV float slots_sum(uint32_t slots, uint32_t filled_mask) {
+  const uint32_t biased = addf(slots, filled_mask & L7);     // e + 127 where filled (<= 145: no carry)
+  return (slot_pow2<0>(biased) + slot_pow2<1>(biased)) + (slot_pow2<2>(biased) + slot_pow2<3>(biased));
+}
+
+// Slide (a,b,c,d) toward a with merging; returns the move score (:254) as an exact float
+// (a sum of at most 8 powers of two <= 2^18).
+G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
   // compaction: bubble the zeros toward d (3+2+1 conditional moves) (:250-251)
   bubble(a, b); bubble(b, c); bubble(c, d);
   bubble(a, b); bubble(b, c);
   bubble(a, b);
   // merges on the compacted line: leftmost pair first, each tile merges once (:252-259)
-  //   m1: a==b!=0;  m2: b==c!=0 and not m1;  m3: c==d!=0 and not m2
-  const uint32_t m1 = ~((a ^ b) + L7) & (b + L7);          // bit 7 only is meaningful
-  const uint32_t m2 = ~((b ^ c) + L7) & (c + L7) & ~m1;
-  const uint32_t m3 = ~((c ^ d) + L7) & (d + L7) & ~m2;
+  //   m1: a==b!=0;  m2: b==c!=0 and not m1;  m3: c==d!=0 and not m2   (bit 7 of each byte)
+  const uint32_t m1 = ~addf(a ^ b, L7) & addf(b, L7);
+  const uint32_t m2 = ~addf(b ^ c, L7) & addf(c, L7) & ~m1;
+  const uint32_t m3 = ~addf(c ^ d, L7) & addf(d, L7) & ~m2;
   const uint32_t M1 = spread(m1), M2 = spread(m2), M3 = spread(m3);
-  a += M1 & K1;                                            // exponent + 1 (value * 2, :253)
-  b = (b & ~M1) + (M2 & K1);
-  c = (c & ~M2) + (M3 & K1);
-  d &= ~M3;
+  // results written directly in their final places (value * 2 == exponent + 1, :253):
+  //   m1&m3: (a+1, c+1, 0, 0)  m1: (a+1, c, d, 0)  m2: (a, b+1, d, 0)  m3: (a, b, c+1, 0)
+  const uint32_t cinc = addf(c, M3 & K1);
+  const uint32_t binc = addf(b, M2 & K1);
+  a = addf(a, M1 & K1);
+  b = (cinc & M1) | (binc & ~M1);
+  c = (M1 & d & ~M3) | (~M1 & ((M2 & d) | (~M2 & cinc)));
+  d &= ~(M1 | M2 | M3);
   // merged exponents: per lane either (m1 and maybe m3) or m2 alone -> two slot words
   const uint32_t sA = (a & M1) | (b & M2);
-  const uint32_t sB = c & M3;
-  // close the holes the merges left at b and/or c, d
-  {
-    const uint32_t m = nzmask(b);
-    b |= c & ~m;
-    c = (c & m) | (d & ~m);
-    d &= m;
-  }
-  bubble(c, d);
-  // score = sum over the 8 slots of 2^e (e != 0).  Shifts use e mod 32 (e <= 18).
-  uint32_t s = (1u << (sA & 31)) + (1u << ((sA >> 8) & 31)) + (1u << ((sA >> 16) & 31)) +
-               (1u << ((sA >> 24) & 31)) + (1u << (sB & 31)) + (1u << ((sB >> 8) & 31)) +
-               (1u << ((sB >> 16) & 31)) + (1u << ((sB >> 24) & 31));
-  // empty slots contributed 2^0 each: subtract them
-  const uint32_t filled = __popc(((M1 | M2) & K1) | (M3 & 0x02020202u));
-  return s - 8u + filled;
+  const uint32_t sB = cinc & M3;
+  return slots_sum(sA, M1 | M2) + slots_sum(sB, M3);
 }
 
 // ---- add_tile (:166-176) under the draw-stream definition ----------------------------
@@ -171,7 +223,7 @@ G2048_DEV uint32_t slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& 
 G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t w,
                          uint32_t enable = 0xFFFFFFFFu) {
   // e_i: bit 7 set where the cell is empty; q_i: 0/1 per byte
-  const uint32_t e0 = ~(r0 + L7) & H, e1 = ~(r1 + L7) & H, e2 = ~(r2 + L7) & H, e3 = ~(r3 + L7) & H;
+  const uint32_t e0 = ~addf(r0, L7) & H, e1 = ~addf(r1, L7) & H, e2 = ~addf(r2, L7) & H, e3 = ~addf(r3, L7) & H;
   const uint32_t q0 = e0 >> 7, q1 = e1 >> 7, q2 = e2 >> 7, q3 = e3 >> 7;
   // inclusive row-major prefix counts of empties, one per byte (<= 16: no carries);
   // byte 3 of each word is the running total, broadcast into the next row's offset
@@ -186,27 +238,31 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
   const uint32_t gk = L7 - k * K1;          // p + gk has bit 7  <=>  p >= k+1
   const uint32_t gk1 = gk - K1;             // p + gk1 has bit 7 <=>  p >= k+2
   const uint32_t tile = ((f < P2_THRESHOLD) ? K1 : 0x02020202u) & enable;   // exponent 1 or 2 (:168)
-  r0 |= spread((p0 + gk) & ~(p0 + gk1) & e0) & tile;
-  r1 |= spread((p1 + gk) & ~(p1 + gk1) & e1) & tile;
-  r2 |= spread((p2 + gk) & ~(p2 + gk1) & e2) & tile;
-  r3 |= spread((p3 + gk) & ~(p3 + gk1) & e3) & tile;
+  r0 |= spread(addf(p0, gk) & ~addf(p0, gk1) & e0) & tile;
+  r1 |= spread(addf(p1, gk) & ~addf(p1, gk1) & e1) & tile;
+  r2 |= spread(addf(p2, gk) & ~addf(p2, gk1) & e2) & tile;
+  r3 |= spread(addf(p3, gk) & ~addf(p3, gk1) & e3) & tile;
   return n;
 }
 
-// reset (:102-111): zero board, two spawns from w1, w2.  Specialised: the first spawn
-// sees 16 empties (k1 = w1 >> 28), the second 15 and skips cell k1.
-G2048_DEV void fresh_board(uint32_t w1, uint32_t w2, uint32_t& r0, uint32_t& r1,
-                                            uint32_t& r2, uint32_t& r3) {
+// reset (:102-111): zero board, two spawns from w1, w2.  Specialised: the first spawn sees
+// 16 empties (k1 = w1 >> 28), the second 15 and skips cell k1.  A board with one tile is one
+// of 32 patterns (16 cells x {2,4}), kept as a uint4 table (shared memory in the kernels):
+// the fresh board is the OR of two entries.
+struct alignas(16) Board4 { uint32_t x, y, z, w; };
+G2048_DEV Board4 one_tile_board(uint32_t entry) {        // entry = cell * 2 + (tile == 4)
+  const uint32_t cell = entry >> 1, v = ((entry & 1u) + 1u) << ((cell & 3u) * 8u), row = cell >> 2;
+  return Board4{row == 0 ? v : 0u, row == 1 ? v : 0u, row == 2 ? v : 0u, row == 3 ? v : 0u};
+}
+G2048_DEV void fresh_board(const Board4* lut, uint32_t w1, uint32_t w2, uint32_t& r0, uint32_t& r1,
+                           uint32_t& r2, uint32_t& r3) {
   const uint32_t k1 = w1 >> 28;
-  const uint32_t t1 = ((w1 << 4) < P2_THRESHOLD) ? 1u : 2u;
+  const uint32_t i1 = 2u * k1 + ((shl<4>(w1) < P2_THRESHOLD) ? 0u : 1u);
   uint32_t k2 = __umulhi(w2, 15u);
-  const uint32_t t2 = ((w2 * 15u) < P2_THRESHOLD) ? 1u : 2u;
   k2 += (k2 >= k1) ? 1u : 0u;
-  // 128-bit one-hot byte insert done as two 64-bit halves
-  const uint64_t v1 = (uint64_t)t1 << ((k1 & 7u) * 8u), v2 = (uint64_t)t2 << ((k2 & 7u) * 8u);
-  const uint64_t lo = ((k1 < 8u) ? v1 : 0ull) | ((k2 < 8u) ? v2 : 0ull);
-  const uint64_t hi = ((k1 < 8u) ? 0ull : v1) | ((k2 < 8u) ? 0ull : v2);
-  r0 = (uint32_t)lo; r1 = (uint32_t)(lo >> 32); r2 = (uint32_t)hi; r3 = (uint32_t)(hi >> 32);
+  const uint32_t i2 = 2u * k2 + (((w2 * 15u) < P2_THRESHOLD) ? 0u : 1u);
+  const Board4 t1 = lut[i1], t2 = lut[i2];
+  r0 = t1.x | t2.x; r1 = t1.y | t2.y; r2 = t1.z | t2.z; r3 = t1.w | t2.w;
 }
 
 // ---- board queries --------------------------------------------------------------------
@@ -262,7 +318,7 @@ G2048_DEV uint32_t count_empty(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r
 
 // ---- one whole step (:76-100) on a board held in registers --------------------------
 struct StepOut {
-  uint32_t score;     // merge score of the move (0 when illegal)
+  float score;        // merge score of the move (0 when illegal), exact
   uint32_t highest;   // exponent of the highest tile after the spawn (valid if requested)
   bool legal;         // False <=> IllegalMove (:91-95)
   bool done;          // terminated
@@ -271,8 +327,9 @@ struct StepOut {
 
 // On return r0..r3 hold the board handed back to the agent: the post-spawn board, or a
 // fresh reset() board when the episode ended and auto_reset is set (SB3 DummyVecEnv).
-G2048_DEV StepOut step_board(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t action,
-                             const Words& w, uint32_t max_tile_exp, bool want_highest, bool auto_reset) {
+G2048_DEV StepOut step_board(const Board4* lut, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                             uint32_t action, const Words& w, uint32_t max_tile_exp, bool want_highest,
+                             bool auto_reset) {
   StepOut o;
   uint32_t a, b, c, d;
   orient(kOrientIn[action], r0, r1, r2, r3, a, b, c, d);
@@ -290,7 +347,7 @@ G2048_DEV StepOut step_board(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t&
   if (max_tile_exp != 0u) end = end || (o.highest == max_tile_exp);                      // :267
   o.done = end || !o.legal;
   o.t0 = r0; o.t1 = r1; o.t2 = r2; o.t3 = r3;
-  if (auto_reset && o.done) fresh_board(w.w1, w.w2, r0, r1, r2, r3);                    // :102-111
+  if (auto_reset && o.done) fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);                    // :102-111
   return o;
 }
 

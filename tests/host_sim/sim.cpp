@@ -10,6 +10,13 @@
 
 using namespace g2048;
 
+static Board4 g_lut[32];
+static const Board4* lut() {
+  static bool init = false;
+  if (!init) { for (uint32_t e = 0; e < 32; ++e) g_lut[e] = one_tile_board(e); init = true; }
+  return g_lut;
+}
+
 static inline void load(const uint8_t* b, uint32_t r[4]) { std::memcpy(r, b, 16); }
 static inline void store(uint8_t* b, const uint32_t r[4]) { std::memcpy(b, r, 16); }
 
@@ -22,17 +29,21 @@ extern "C" int sim_step(const G2048StepArgs* p) {
       const uint32_t* f = p->forced_draws + 4 * i;
       w = Words{f[0], f[1], f[2], f[3]};
     } else {
-      w = draw_words(p->seed, p->env_id_base + i, p->step_counter ? *p->step_counter : p->step_index, 0);
+      RoundKeys rk;
+      make_round_keys(p->seed, rk);
+      const uint64_t env = p->env_id_base + i, idx = p->step_counter ? *p->step_counter : p->step_index;
+      w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)env,
+                           (uint32_t)(env >> 32) & 0x7FFFFFFFu, rk);
     }
     const bool auto_reset = (p->flags & G2048_FLAG_AUTO_RESET) != 0;
-    StepOut o = step_board(r[0], r[1], r[2], r[3], p->actions[i] & 3u, w, p->max_tile_exp,
+    StepOut o = step_board(lut(), r[0], r[1], r[2], r[3], p->actions[i] & 3u, w, p->max_tile_exp,
                            p->highest_exp != nullptr, auto_reset);
     store(p->boards + 16 * i, r);
-    p->rewards[i] = o.legal ? (float)o.score : p->illegal_move_reward;
+    p->rewards[i] = o.legal ? o.score : p->illegal_move_reward;
     p->dones[i] = o.done;
     if (p->illegal) p->illegal[i] = !o.legal;
     if (p->highest_exp) p->highest_exp[i] = (uint8_t)o.highest;
-    uint32_t es = p->ep_score ? p->ep_score[i] + o.score : 0, el = p->ep_len ? p->ep_len[i] + 1 : 0;
+    uint32_t es = p->ep_score ? p->ep_score[i] + (uint32_t)o.score : 0, el = p->ep_len ? p->ep_len[i] + 1 : 0;
     if (o.done) {
       const uint32_t t[4] = {o.t0, o.t1, o.t2, o.t3};
       if (p->terminal_boards) store(p->terminal_boards + 16 * i, t);
@@ -54,7 +65,7 @@ extern "C" int sim_reset(uint8_t* boards, const uint8_t* mask, uint64_t n, uint6
     if (mask && !mask[i]) continue;
     Words w = draw_words(seed, base + i, reset_index, 1);
     uint32_t r[4];
-    fresh_board(w.w1, w.w2, r[0], r[1], r[2], r[3]);
+    fresh_board(lut(), w.w1, w.w2, r[0], r[1], r[2], r[3]);
     store(boards + 16 * i, r);
   }
   return 0;
@@ -79,7 +90,7 @@ extern "C" int sim_move(const uint8_t* in, uint8_t* out, const uint8_t* dirs, ui
     const uint32_t act = dirs[i] & 3u;
     orient(kOrientIn[act], r[0], r[1], r[2], r[3], a, b, c, d);
     const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
-    const uint32_t s = slide_merge(a, b, c, d);
+    const uint32_t s = (uint32_t)slide_merge(a, b, c, d);
     orient(kOrientOut[act], a, b, c, d, r[0], r[1], r[2], r[3]);
     if (out) store(out + 16 * i, r);
     if (scores) scores[i] = s;
