@@ -65,6 +65,8 @@ class BatchedGame2048:
             raise G2048Error("BatchedGame2048 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.env_id_base = int(env_id_base)
         self.seed = int(seed) & (2**64 - 1)
@@ -93,6 +95,7 @@ class BatchedGame2048:
         self.final_score = torch.zeros(n, **i32) if ep else None
         self.final_len = torch.zeros(n, **i32) if ep else None
         self._step_counter = None      # device uint64 step index (use_device_step_counter)
+        self._args = None              # cached G2048StepArgs, rebuilt when a knob changes
 
     # -- knobs (reference :61-73) ------------------------------------------------------
     def set_illegal_move_reward(self, reward):
@@ -153,32 +156,58 @@ class BatchedGame2048:
         return self.boards
 
     # -- step (:76-100) ----------------------------------------------------------------
+    def _build_step_args(self):
+        a = StepArgs(self._ptr(self.boards), None, self._ptr(self.rewards), self._ptr(self._dones),
+                     self._ptr(self._illegal), self._ptr(self.highest_exp), self._ptr(self.legal_mask),
+                     self._ptr(self.terminal_boards), self._ptr(self.ep_score), self._ptr(self.ep_len),
+                     self._ptr(self.final_score), self._ptr(self.final_len), None, self._ptr(self._step_counter),
+                     self.num_envs, self.env_id_base, self.seed, self.step_index,
+                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
+        self._args = a
+        self._args_ref = C.byref(a)
+        self._args_key = (self.seed, self.env_id_base, self.illegal_move_reward, self.max_tile_exp,
+                          self.auto_reset, None if self._step_counter is None else self._step_counter.data_ptr())
+        self._result = StepResult(self.boards, self.rewards, self._dones.view(torch.bool),
+                                  None if self._illegal is None else self._illegal.view(torch.bool),
+                                  self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
+                                  self.final_len)
+
     def step(self, actions, forced_draws=None):
-        """One env step for every board.  `actions`: uint8/int tensor [n] on any device."""
+        """One env step for every board.  `actions`: uint8/int tensor [n] on any device.
+
+        The returned StepResult holds the env's own output tensors (overwritten by the next
+        step); clone what must outlive it."""
         n = self.num_envs
         if isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device \
                 and actions.is_contiguous() and actions.shape == (n,):
             act = actions                       # fast path: no validation pass over the batch
         else:
             act = self._as_u8(actions, (n,), "actions")
+        key = (self.seed, self.env_id_base, self.illegal_move_reward, self.max_tile_exp, self.auto_reset,
+               None if self._step_counter is None else self._step_counter.data_ptr())
+        if self._args is None or key != self._args_key:
+            self._build_step_args()
+        a = self._args
+        a.actions = act.data_ptr()
+        a.step_index = self.step_index
         fd = None
         if forced_draws is not None:
             fd = torch.as_tensor(forced_draws).to(self.device).contiguous()
             if fd.dtype != torch.uint32 or tuple(fd.shape) != (n, 4):
                 raise ValueError("forced_draws must be uint32 [n,4]")
-        a = StepArgs(self._ptr(self.boards), self._ptr(act), self._ptr(self.rewards), self._ptr(self._dones),
-                     self._ptr(self._illegal), self._ptr(self.highest_exp), self._ptr(self.legal_mask),
-                     self._ptr(self.terminal_boards), self._ptr(self.ep_score), self._ptr(self.ep_len),
-                     self._ptr(self.final_score), self._ptr(self.final_len), self._ptr(fd), self._ptr(self._step_counter),
-                     n, self.env_id_base, self.seed, self.step_index,
-                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
-        with torch.cuda.device(self.device):
-            check(self.lib.g2048_step(C.byref(a), self._stream()))
+            a.forced_draws = fd.data_ptr()
+        else:
+            a.forced_draws = None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if torch.cuda.current_device() == self.device.index:
+            rc = self.lib.g2048_step(self._args_ref, stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc = self.lib.g2048_step(self._args_ref, stream)
+        if rc:
+            check(rc)
         self.step_index += 1      # host mirror; the device counter (if any) is bumped on the stream
-        return StepResult(self.boards, self.rewards, self._dones.view(torch.bool),
-                          None if self._illegal is None else self._illegal.view(torch.bool),
-                          self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
-                          self.final_len)
+        return self._result
 
     def use_device_step_counter(self, enable=True):
         """Keep the step index in device memory (bumped by a 1-thread kernel after each step) so

@@ -41,8 +41,21 @@ static int cuda_fail(cudaError_t e, const char* what) {
 // launch geometry: 256-thread CTAs, grid-stride, at most kCtasPerSm resident CTAs per SM
 // so large batches run as one persistent wave over the 148 SMs.
 // ------------------------------------------------------------------------------------
-constexpr int kThreads = 256;
-constexpr int kCtasPerSm = 8;
+// Tunables (overridable with -D for scripts/kernel_variants.py experiments)
+#ifndef G2048_THREADS
+#define G2048_THREADS 512
+#endif
+#ifndef G2048_CTAS_PER_SM
+#define G2048_CTAS_PER_SM 2
+#endif
+#ifndef G2048_PDL            // programmatic dependent launch: overlap this launch's ramp with
+#define G2048_PDL 1          // the previous kernel's tail (griddepcontrol.wait guards all loads)
+#endif
+#ifndef G2048_PREFETCH       // load the next iteration's board/action before computing this one
+#define G2048_PREFETCH 1
+#endif
+constexpr int kThreads = G2048_THREADS;
+constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 
 static int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -95,15 +108,35 @@ __device__ __forceinline__ const Board4* make_reset_lut(Board4* s_lut) {
 }
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
   __shared__ Board4 s_lut[32];
+#if G2048_PDL
+  // Let the next launch in the stream start its ramp as soon as our CTAs retire; everything
+  // before griddepcontrol.wait touches no global memory, so it overlaps the previous kernel.
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
   const Board4* lut = make_reset_lut(s_lut);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
   const uint32_t n = (uint32_t)p.n, stride = gridDim.x * kThreads;     // n < 2^32 (checked by the host)
+  uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+#if G2048_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  if (i >= n) return;
   const uint64_t step_index = p.step_counter ? *p.step_counter : p.step_index;
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    uint4 bd = p.boards[i];
-    const uint32_t action = p.actions[i] & 3u;
+  uint4 bd = p.boards[i];
+  uint32_t action = p.actions[i];
+  while (true) {
+#if G2048_PREFETCH
+    const uint32_t i_next = i + stride;
+    const bool more = i_next < n && i_next > i;
+    uint4 bd_next = bd;
+    uint32_t action_next = 0;
+    if (more) {
+      bd_next = p.boards[i_next];
+      action_next = p.actions[i_next];
+    }
+#endif
     Words w;
     if (EXTRAS && p.forced_draws) {
       const uint4 f = p.forced_draws[i];
@@ -113,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p
       w = philox4x32_10_rk((uint32_t)step_index, (uint32_t)(step_index >> 32), (uint32_t)env,
                            (uint32_t)(env >> 32) & 0x7FFFFFFFu, p.rk);
     }
-    const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action, w, p.max_tile_exp,
+    const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action & 3u, w, p.max_tile_exp,
                                  EXTRAS && p.highest_exp != nullptr, auto_reset);
     p.boards[i] = bd;
     p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
@@ -134,6 +167,14 @@ __global__ void __launch_bounds__(kThreads) g2048_step_kernel(const StepParams p
       if (p.ep_len) p.ep_len[i] = el;
       if (p.legal_mask) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
     }
+#if G2048_PREFETCH
+    if (!more) break;
+    i = i_next; bd = bd_next; action = action_next;
+#else
+    const uint32_t i_next = i + stride;
+    if (i_next >= n || i_next <= i) break;
+    i = i_next; bd = p.boards[i]; action = p.actions[i];
+#endif
   }
 }
 
@@ -355,8 +396,21 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   const bool extras = a->illegal || a->highest_exp || a->legal_mask || a->terminal_boards || a->ep_score ||
                       a->ep_len || a->final_score || a->final_len || a->forced_draws;
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (extras) g2048_step_kernel<true><<<grid_for(a->n), kThreads, 0, s>>>(p);
-  else        g2048_step_kernel<false><<<grid_for(a->n), kThreads, 0, s>>>(p);
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid_for(a->n));
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = s;
+#if G2048_PDL
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#endif
+  const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<true>, p)
+                                : cudaLaunchKernelEx(&cfg, g2048_step_kernel<false>, p);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_kernel)");
   if (a->step_counter) g2048_bump_counter_kernel<<<1, 1, 0, s>>>(a->step_counter);
   return launch_check("g2048_step_kernel");
 }

@@ -61,6 +61,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 inline uint32_t addf(uint32_t x, uint32_t y) { return x + y; }
 template <int S> inline uint32_t shr(uint32_t x) { return x >> S; }
 template <int S> inline uint32_t shl(uint32_t x) { return x << S; }
+inline uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
 #else
 __constant__ uint32_t kOne = 1u;
 __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
@@ -70,6 +71,12 @@ __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
 }
 template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
 template <int S> __device__ __forceinline__ uint32_t shl(uint32_t x) { return x * (1u << S); }
+// hi32(a * b) + c in one IMAD.HI
+__device__ __forceinline__ uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 #endif
 // 0xFF in every byte whose bit 7 is set, else 0x00.
 G2048_DEV uint32_t spread(uint32_t x) { return prmt(x, 0u, 0xBA98u); }
@@ -173,7 +180,7 @@ G2048_DEV void bubble(uint32_t& x, uint32_t& y) {
 template <int K> G2048_DEV float slot_pow2(uint32_t biased) {
   constexpr uint32_t EXPF = 0x7F800000u;
   uint32_t bits;
-  if (K == 3) bits = (biased >> 1) & EXPF;
+  if (K == 3) bits = shr<1>(biased) & EXPF;
   else bits = shl<23 - 8 * K>(biased) & EXPF;
 #ifdef G2048_HOST_SIM
   float f;
@@ -224,24 +231,28 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
                          uint32_t enable = 0xFFFFFFFFu) {
   // e_i: bit 7 set where the cell is empty; q_i: 0/1 per byte
   const uint32_t e0 = ~addf(r0, L7) & H, e1 = ~addf(r1, L7) & H, e2 = ~addf(r2, L7) & H, e3 = ~addf(r3, L7) & H;
-  const uint32_t q0 = e0 >> 7, q1 = e1 >> 7, q2 = e2 >> 7, q3 = e3 >> 7;
+  const uint32_t q0 = shr<7>(e0), q1 = shr<7>(e1), q2 = shr<7>(e2), q3 = shr<7>(e3);
   // inclusive row-major prefix counts of empties, one per byte (<= 16: no carries);
   // byte 3 of each word is the running total, broadcast into the next row's offset
   const uint32_t p0 = q0 * K1;
   const uint32_t p1 = q1 * K1 + prmt(p0, 0u, 0x3333u);
   const uint32_t p2 = q2 * K1 + prmt(p1, 0u, 0x3333u);
   const uint32_t p3 = q3 * K1 + prmt(p2, 0u, 0x3333u);
-  const uint32_t n = p3 >> 24;
+  const uint32_t n = shr<24>(p3);
   const uint32_t k = __umulhi(w, n);
   const uint32_t f = w * n;
   // target = the cell with prefix == k+1 that is empty:  (p > k) and not (p > k+1)
   const uint32_t gk = L7 - k * K1;          // p + gk has bit 7  <=>  p >= k+1
   const uint32_t gk1 = gk - K1;             // p + gk1 has bit 7 <=>  p >= k+2
-  const uint32_t tile = ((f < P2_THRESHOLD) ? K1 : 0x02020202u) & enable;   // exponent 1 or 2 (:168)
-  r0 |= spread(addf(p0, gk) & ~addf(p0, gk1) & e0) & tile;
-  r1 |= spread(addf(p1, gk) & ~addf(p1, gk1) & e1) & tile;
-  r2 |= spread(addf(p2, gk) & ~addf(p2, gk1) & e2) & tile;
-  r3 |= spread(addf(p3, gk) & ~addf(p3, gk1) & e3) & tile;
+  // The target flag t_i has bit 7 of exactly one byte set (e_i is clean).  Shifting it right by 7
+  // (tile 2, exponent 1) or 6 (tile 4, exponent 2) gives the tile byte; the cell is empty, so adding
+  // equals inserting.  The shift is the high half of t_i * 2^25 / 2^26: one IMAD.HI per row, and a
+  // zero multiplier (illegal move: no tile, :91-95) disables the spawn.
+  const uint32_t mult = ((f < P2_THRESHOLD) ? (1u << 25) : (1u << 26)) & enable;                  // :168
+  r0 = madhi(addf(p0, gk) & ~addf(p0, gk1) & e0, mult, r0);
+  r1 = madhi(addf(p1, gk) & ~addf(p1, gk1) & e1, mult, r1);
+  r2 = madhi(addf(p2, gk) & ~addf(p2, gk1) & e2, mult, r2);
+  r3 = madhi(addf(p3, gk) & ~addf(p3, gk1) & e3, mult, r3);
   return n;
 }
 
