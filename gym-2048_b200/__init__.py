@@ -12,9 +12,10 @@ CPU fallback.
 from . import _lib
 from ._lib import G2048Error, build
 from .batched import ALL_OUTPUTS, BatchedGame2048, HostSteppedEnv, StepResult, shard_range, tile_to_exp
+from .stats import EpisodeStats
 from .env import Game2048Env, IllegalMove, register, stack
 from .vec_env import Game2048VecEnv
 
 __all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Game2048VecEnv", "IllegalMove",
-           "stack", "register", "shard_range", "tile_to_exp", "build", "G2048Error", "ALL_OUTPUTS"]
+           "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS"]
 __version__ = "0.1.0"

@@ -54,6 +54,9 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #ifndef G2048_PREFETCH       // load the next iteration's board/action before computing this one
 #define G2048_PREFETCH 1
 #endif
+#ifndef G2048_PERSISTENT     // 1: grid-stride loop over a grid sized to the SM count; 0: one board per thread
+#define G2048_PERSISTENT 1
+#endif
 constexpr int kThreads = G2048_THREADS;
 constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 
@@ -107,6 +110,42 @@ __device__ __forceinline__ const Board4* make_reset_lut(Board4* s_lut) {
   return s_lut;
 }
 
+// One board through Game2048Env.step and out to memory.
+template <bool EXTRAS>
+__device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint4 bd,
+                                               uint32_t action, uint64_t step_index, bool auto_reset) {
+  Words w;
+  if (EXTRAS && p.forced_draws) {
+    const uint4 f = p.forced_draws[i];
+    w = Words{f.x, f.y, f.z, f.w};
+  } else {
+    const uint64_t env = p.env_id_base + i;
+    w = philox4x32_10_rk((uint32_t)step_index, (uint32_t)(step_index >> 32), (uint32_t)env,
+                         (uint32_t)(env >> 32) & 0x7FFFFFFFu, p.rk);
+  }
+  const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action & 3u, w, p.max_tile_exp,
+                               EXTRAS && p.highest_exp != nullptr, auto_reset);
+  p.boards[i] = bd;
+  p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
+  p.dones[i] = o.done ? 1 : 0;
+  if (EXTRAS) {
+    if (p.illegal) p.illegal[i] = o.legal ? 0 : 1;                   // :82, :93
+    if (p.highest_exp) p.highest_exp[i] = (uint8_t)o.highest;        // :97
+    uint32_t es = 0, el = 0;
+    if (p.ep_score) es = p.ep_score[i] + (uint32_t)o.score;          // :86
+    if (p.ep_len) el = p.ep_len[i] + 1u;
+    if (o.done) {
+      if (p.terminal_boards) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
+      if (p.final_score) p.final_score[i] = es;
+      if (p.final_len) p.final_len[i] = el;
+      if (auto_reset) es = el = 0u;
+    }
+    if (p.ep_score) p.ep_score[i] = es;
+    if (p.ep_len) p.ep_len[i] = el;
+    if (p.legal_mask) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
+  }
+}
+
 template <bool EXTRAS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
   __shared__ Board4 s_lut[32];
@@ -124,58 +163,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
   if (i >= n) return;
   const uint64_t step_index = p.step_counter ? *p.step_counter : p.step_index;
+#if !G2048_PERSISTENT
+  step_and_store<EXTRAS>(p, lut, i, p.boards[i], p.actions[i], step_index, auto_reset);
+#elif !G2048_PREFETCH
+  for (; i < n; i += stride) {
+    step_and_store<EXTRAS>(p, lut, i, p.boards[i], p.actions[i], step_index, auto_reset);
+    if (i + stride <= i) break;
+  }
+#else
+  // Grid-stride loop, software-pipelined one board ahead.  (Unrolling by two to avoid the
+  // register copies was measured slower: the doubled body no longer fits the L0 I-cache.)
   uint4 bd = p.boards[i];
   uint32_t action = p.actions[i];
   while (true) {
-#if G2048_PREFETCH
     const uint32_t i_next = i + stride;
     const bool more = i_next < n && i_next > i;
-    uint4 bd_next = bd;
+    uint4 bd_next;
     uint32_t action_next = 0;
-    if (more) {
-      bd_next = p.boards[i_next];
-      action_next = p.actions[i_next];
-    }
-#endif
-    Words w;
-    if (EXTRAS && p.forced_draws) {
-      const uint4 f = p.forced_draws[i];
-      w = Words{f.x, f.y, f.z, f.w};
-    } else {
-      const uint64_t env = p.env_id_base + i;
-      w = philox4x32_10_rk((uint32_t)step_index, (uint32_t)(step_index >> 32), (uint32_t)env,
-                           (uint32_t)(env >> 32) & 0x7FFFFFFFu, p.rk);
-    }
-    const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action & 3u, w, p.max_tile_exp,
-                                 EXTRAS && p.highest_exp != nullptr, auto_reset);
-    p.boards[i] = bd;
-    p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
-    p.dones[i] = o.done ? 1 : 0;
-    if (EXTRAS) {
-      if (p.illegal) p.illegal[i] = o.legal ? 0 : 1;                   // :82, :93
-      if (p.highest_exp) p.highest_exp[i] = (uint8_t)o.highest;        // :97
-      uint32_t es = 0, el = 0;
-      if (p.ep_score) es = p.ep_score[i] + (uint32_t)o.score;          // :86
-      if (p.ep_len) el = p.ep_len[i] + 1u;
-      if (o.done) {
-        if (p.terminal_boards) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
-        if (p.final_score) p.final_score[i] = es;
-        if (p.final_len) p.final_len[i] = el;
-        if (auto_reset) es = el = 0u;
-      }
-      if (p.ep_score) p.ep_score[i] = es;
-      if (p.ep_len) p.ep_len[i] = el;
-      if (p.legal_mask) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
-    }
-#if G2048_PREFETCH
+    if (more) { bd_next = p.boards[i_next]; action_next = p.actions[i_next]; }
+    step_and_store<EXTRAS>(p, lut, i, bd, action, step_index, auto_reset);
     if (!more) break;
     i = i_next; bd = bd_next; action = action_next;
-#else
-    const uint32_t i_next = i + stride;
-    if (i_next >= n || i_next <= i) break;
-    i = i_next; bd = p.boards[i]; action = p.actions[i];
-#endif
   }
+#endif
 }
 
 __global__ void g2048_bump_counter_kernel(uint64_t* counter) { *counter += 1ull; }
@@ -398,7 +408,11 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
+#if G2048_PERSISTENT
   cfg.gridDim = dim3(grid_for(a->n));
+#else
+  cfg.gridDim = dim3((unsigned)((a->n + kThreads - 1) / kThreads));
+#endif
   cfg.blockDim = dim3(kThreads);
   cfg.stream = s;
 #if G2048_PDL
