@@ -196,10 +196,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self, t_start, t_end):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.05)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -289,11 +294,13 @@ def run_ours(args):
             gm.step(pool[t % args.action_pool])
     torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(W):
         games[i % R].step(pool[i % args.action_pool])
     torch.cuda.synchronize()
+    if sampler:
+        sampler.wait_first_sample()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start = time.perf_counter()
@@ -354,10 +361,11 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cb = {}
         if reference_available():
-            v, wall = time_reference(cores, args.ref_steps_per_proc * 4)
+            per = args.ref_steps_per_proc * 30          # ~15 s of CPU work per core's worth of processes
+            v, wall = time_reference(cores, per)
             cb = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                  "sample": "%d processes x 1 unmodified reference env x %d step() calls, uniform-random actions"
-                            % (cores, args.ref_steps_per_proc * 4), "wall_s": wall}
+                  "sample": "%d processes x 1 unmodified reference env x %d step() calls, uniform-random "
+                            "actions, reset() on terminated" % (cores, per), "wall_s": wall}
         port = time_port(1 << 18, 8, cores)
         if not cb:
             cb = {"value": port, "unit": UNIT, "cores": cores, "kind": "port",
@@ -393,7 +401,7 @@ def main():
         budget_calls = 120000                      # ~6 s per process at ~20k steps/s
         args.ref_steps_per_proc = max(200, min(args.ref_steps_per_proc, budget_calls // max(args.steps, 1)))
         return run_reference(args)
-    args.steps = 20000 if args.steps is None else args.steps
+    args.steps = 50000 if args.steps is None else args.steps
     args.warmup = 200 if args.warmup is None else max(args.warmup, 3)
     return run_ours(args)
 
