@@ -5,6 +5,7 @@ Public surface:
   HostSteppedEnv    host-buffer handle of the C ABI (actions/results in pinned host memory)
   Game2048Env       single-env class with the reference's gymnasium + game API (env.py)
   Game2048VecEnv    Stable-Baselines3-style VecEnv adapter over BatchedGame2048 (vec_env.py)
+  Transitions / TransitionRecorder  the reference's transition table + CSV schema on the GPU (transitions.py)
   stack, IllegalMove  as in the reference module
 The CUDA extension is built in-tree by `_lib.build()` (nvcc, sm_100a); nothing here has a
 CPU fallback.
@@ -15,7 +16,9 @@ from .batched import ALL_OUTPUTS, BatchedGame2048, HostSteppedEnv, StepResult, s
 from .stats import EpisodeStats
 from .env import Game2048Env, IllegalMove, register, stack
 from .vec_env import Game2048VecEnv
+from .transitions import TransitionRecorder, Transitions
 
 __all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Game2048VecEnv", "IllegalMove",
-           "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS"]
+           "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS",
+           "Transitions", "TransitionRecorder"]
 __version__ = "0.1.0"

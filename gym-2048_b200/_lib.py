@@ -11,12 +11,13 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "libg2048.so")
-SOURCES = [os.path.join(_PKG, "csrc", "g2048.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_ROOT, "include", "g2048.h")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("g2048.cu", "g2048_data.cu", "g2048_csv.cpp")]
+HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_PKG, "csrc", "g2048_internal.h"),
+           os.path.join(_ROOT, "include", "g2048.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_AUTO_RESET = 1
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
@@ -25,6 +26,8 @@ EXPORTS = [
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
+    "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return",
+    "g2048_csv_export", "g2048_csv_rows", "g2048_csv_import",
 ]
 
 
@@ -44,7 +47,7 @@ class StepArgs(C.Structure):
         ("n", C.c_uint64), ("env_id_base", C.c_uint64), ("seed", C.c_uint64),
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("boards_out", C.c_void_p),
     ]
 
 
@@ -127,6 +130,13 @@ def lib():
     L.g2048_env_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.g2048_env_set_boards_host.argtypes = [vp, vp]
     L.g2048_env_step_index.argtypes = [vp]
+    L.g2048_sample_actions.argtypes = [vp, vp, u64, u64, u64, u64, vp]
+    L.g2048_symmetry.argtypes = [vp, vp, vp, vp, vp, vp, u64, C.c_int, C.c_int, vp]
+    L.g2048_augment.argtypes = [vp] * 5 + [u64] + [vp] * 6
+    L.g2048_discounted_return.argtypes = [vp, vp, vp, u64, C.c_double, vp]
+    L.g2048_csv_export.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, u64, C.c_int]
+    L.g2048_csv_rows.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_int)]
+    L.g2048_csv_import.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, u64]
     if L.g2048_abi_version() != ABI_VERSION:
         raise G2048Error("libg2048.so ABI %d != binding ABI %d" % (L.g2048_abi_version(), ABI_VERSION))
     _lib = L

@@ -162,7 +162,7 @@ class BatchedGame2048:
                      self._ptr(self.terminal_boards), self._ptr(self.ep_score), self._ptr(self.ep_len),
                      self._ptr(self.final_score), self._ptr(self.final_len), None, self._ptr(self._step_counter),
                      self.num_envs, self.env_id_base, self.seed, self.step_index,
-                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
+                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0, None)
         self._args = a
         self._args_ref = C.byref(a)
         self._args_key = (self.seed, self.env_id_base, self.illegal_move_reward, self.max_tile_exp,
@@ -172,8 +172,19 @@ class BatchedGame2048:
                                   self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
                                   self.final_len)
 
-    def step(self, actions, forced_draws=None):
+    def _check_board_buffer(self, t, what):
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.device == self.device
+                and t.is_contiguous() and tuple(t.shape) == (self.num_envs, 16)):
+            raise ValueError("%s must be a contiguous uint8 [%d,16] tensor on %s" % (what, self.num_envs, self.device))
+        return t
+
+    def step(self, actions, forced_draws=None, boards_out=None, terminal_out=None):
         """One env step for every board.  `actions`: uint8/int tensor [n] on any device.
+
+        boards_out: step OUT OF PLACE — the boards handed back to the agent are written there
+        and become the env's live state (`self.boards`), the previous buffer keeps the pre-step
+        boards.  A trajectory buffer [T+1,n,16] is filled by passing slice t+1 at step t, with no
+        copy.  terminal_out: where this step's terminal boards go instead of `terminal_boards`.
 
         The returned StepResult holds the env's own output tensors (overwritten by the next
         step); clone what must outlive it."""
@@ -190,6 +201,12 @@ class BatchedGame2048:
         a = self._args
         a.actions = act.data_ptr()
         a.step_index = self.step_index
+        a.boards = self.boards.data_ptr()
+        a.boards_out = None if boards_out is None else self._check_board_buffer(boards_out, "boards_out").data_ptr()
+        if terminal_out is not None:
+            a.terminal_boards = self._check_board_buffer(terminal_out, "terminal_out").data_ptr()
+        elif self.terminal_boards is not None:
+            a.terminal_boards = self.terminal_boards.data_ptr()
         fd = None
         if forced_draws is not None:
             fd = torch.as_tensor(forced_draws).to(self.device).contiguous()
@@ -207,7 +224,28 @@ class BatchedGame2048:
         if rc:
             check(rc)
         self.step_index += 1      # host mirror; the device counter (if any) is bumped on the stream
-        return self._result
+        res = self._result
+        if boards_out is not None:
+            self.boards = boards_out
+        res.boards = self.boards
+        res.terminal_boards = terminal_out if terminal_out is not None else self.terminal_boards
+        return res
+
+    def sample_actions(self, legal=False, out=None):
+        """Uniform-random actions for the NEXT step, drawn on the device from word 3 of that
+        step's Philox block (reference: `random.randint(0, 3)`, train.py:119).  legal=True draws
+        uniformly among the legal moves of the live boards (needs the `legal_mask` output)."""
+        if legal and self.legal_mask is None:
+            raise ValueError("sample_actions(legal=True) needs the 'legal_mask' output")
+        if self._step_counter is not None:
+            raise G2048Error("sample_actions is not available with a device-side step counter")
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.g2048_sample_actions(self._ptr(self.legal_mask) if legal else None, self._ptr(out),
+                                                self.num_envs, self.env_id_base, self.seed, self.step_index,
+                                                self._stream()))
+        return out
 
     def use_device_step_counter(self, enable=True):
         """Keep the step index in device memory (bumped by a 1-thread kernel after each step) so

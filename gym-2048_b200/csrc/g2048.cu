@@ -13,6 +13,7 @@
 
 #include "../../include/g2048.h"
 #include "g2048_device.cuh"
+#include "g2048_internal.h"
 
 namespace g2048 {
 
@@ -21,30 +22,22 @@ namespace g2048 {
 // ------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
   return code;
 }
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
   return fail(G2048_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
-#define G2048_CUDA(call)                                  \
-  do {                                                    \
-    cudaError_t e_ = (call);                              \
-    if (e_ != cudaSuccess) return cuda_fail(e_, #call);   \
-  } while (0)
 
 // ------------------------------------------------------------------------------------
 // launch geometry: 256-thread CTAs, grid-stride, at most kCtasPerSm resident CTAs per SM
 // so large batches run as one persistent wave over the 148 SMs.
 // ------------------------------------------------------------------------------------
 // Tunables (overridable with -D for scripts/kernel_variants.py experiments)
-#ifndef G2048_THREADS
-#define G2048_THREADS 512
-#endif
 #ifndef G2048_CTAS_PER_SM
 #define G2048_CTAS_PER_SM 2
 #endif
@@ -57,8 +50,8 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #ifndef G2048_PERSISTENT     // 1: grid-stride loop over a grid sized to the SM count; 0: one board per thread
 #define G2048_PERSISTENT 1
 #endif
-constexpr int kThreads = G2048_THREADS;
 constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
+static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");
 
 static int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -70,7 +63,7 @@ static int sm_count() {
   }
   return cached;
 }
-static unsigned grid_for(uint64_t n) {
+unsigned grid_for(uint64_t n) {
   const uint64_t need = (n + kThreads - 1) / kThreads;
   const uint64_t cap = (uint64_t)sm_count() * kCtasPerSm;
   return (unsigned)(need < cap ? need : cap);
@@ -80,7 +73,8 @@ static unsigned grid_for(uint64_t n) {
 // kernels
 // ------------------------------------------------------------------------------------
 struct StepParams {
-  uint4* boards;
+  const uint4* boards;
+  uint4* boards_out;            // == boards for an in-place step
   const uint8_t* actions;
   float* rewards;
   uint8_t* dones;
@@ -125,7 +119,7 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
   }
   const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action & 3u, w, p.max_tile_exp,
                                EXTRAS && p.highest_exp != nullptr, auto_reset);
-  p.boards[i] = bd;
+  p.boards_out[i] = bd;
   p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
   p.dones[i] = o.done ? 1 : 0;
   if (EXTRAS) {
@@ -333,9 +327,7 @@ g2048_philox_kernel(const uint4* ctr, uint32_t k0, uint32_t k1, uint4* out, uint
   }
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-static int launch_check(const char* name) {
+int launch_check(const char* name) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, name);
   return G2048_OK;
@@ -376,12 +368,15 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   if (a->n == 0) return G2048_OK;
   if (!a->boards || !a->actions || !a->rewards || !a->dones)
     return fail(G2048_ERR_INVALID, "g2048_step: boards, actions, rewards and dones are required");
-  if (!aligned16(a->boards) || !aligned16(a->terminal_boards) || !aligned16(a->forced_draws))
-    return fail(G2048_ERR_ALIGN, "g2048_step: boards / terminal_boards / forced_draws must be 16-byte aligned");
+  if (!aligned16(a->boards) || !aligned16(a->boards_out) || !aligned16(a->terminal_boards) ||
+      !aligned16(a->forced_draws))
+    return fail(G2048_ERR_ALIGN,
+                "g2048_step: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned");
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
   if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
   StepParams p;
-  p.boards = reinterpret_cast<uint4*>(a->boards);
+  p.boards = reinterpret_cast<const uint4*>(a->boards);
+  p.boards_out = reinterpret_cast<uint4*>(a->boards_out ? a->boards_out : a->boards);
   p.actions = a->actions;
   p.rewards = a->rewards;
   p.dones = a->dones;

@@ -20,7 +20,7 @@
 #define G2048_CONST static const
 #else
 #define G2048_DEV __device__ __forceinline__
-#define G2048_CONST __constant__
+#define G2048_CONST static __constant__      // one copy per translation unit (no relocatable device code)
 #endif
 
 namespace g2048 {
@@ -63,7 +63,7 @@ template <int S> inline uint32_t shr(uint32_t x) { return x >> S; }
 template <int S> inline uint32_t shl(uint32_t x) { return x << S; }
 inline uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
 #else
-__constant__ uint32_t kOne = 1u;
+static __constant__ uint32_t kOne = 1u;
 __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
   uint32_t d;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(kOne), "r"(y));
@@ -325,6 +325,37 @@ G2048_DEV uint32_t legal_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3
 
 G2048_DEV uint32_t count_empty(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   return 16u - __popc((r0 + L7) & H) - __popc((r1 + L7) & H) - __popc((r2 + L7) & H) - __popc((r3 + L7) & H);
+}
+
+// ---- board symmetries of the reference's training_data.py (:257-279) ------------------------
+// hflip: np.flip(x, 2) — every row reversed; swaps actions 1 and 3 (:262-268).
+G2048_DEV void board_hflip(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  r0 = prmt(r0, 0u, 0x0123u); r1 = prmt(r1, 0u, 0x0123u); r2 = prmt(r2, 0u, 0x0123u); r3 = prmt(r3, 0u, 0x0123u);
+}
+G2048_DEV uint32_t action_hflip(uint32_t a) { return (a & 1u) ? (a ^ 2u) : a; }
+// rotate(1): np.rot90(x, k=1, axes=(2,1)) on [n,4,4] = a clockwise quarter turn, new[r][c] =
+// old[3-c][r]: new row R is column R of the old board read bottom to top; action + 1 mod 4 (:277).
+template <int R> G2048_DEV uint32_t rot1_row(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  constexpr uint32_t sel = (uint32_t)R | ((4u + R) << 4);   // byte0 = first[R], byte1 = second[R]
+  const uint32_t lo = prmt(r3, r2, sel);                     // old[3][R], old[2][R]
+  const uint32_t hi = prmt(r1, r0, sel);                     // old[1][R], old[0][R]
+  return prmt(lo, hi, 0x5410u);
+}
+G2048_DEV void board_rot1(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  const uint32_t n0 = rot1_row<0>(r0, r1, r2, r3), n1 = rot1_row<1>(r0, r1, r2, r3);
+  const uint32_t n2 = rot1_row<2>(r0, r1, r2, r3), n3 = rot1_row<3>(r0, r1, r2, r3);
+  r0 = n0; r1 = n1; r2 = n2; r3 = n3;
+}
+
+// ---- random policies (train.py:119 random.randint(0, 3); random-legal of BASELINE config 4) ---
+// The k-th set bit of the 4-bit mask of allowed actions (all four when the mask is empty),
+// k = hi32(w * popcount): uniform over the allowed set.
+G2048_DEV uint32_t pick_action(uint32_t mask, uint32_t w) {
+  uint32_t m = mask & 15u;
+  if (m == 0u) m = 15u;
+  uint32_t k = __umulhi(w, __popc(m));
+  for (; k > 0u; --k) m &= m - 1u;       // drop the k lowest allowed actions
+  return __popc((m & (0u - m)) - 1u);    // index of the lowest remaining one
 }
 
 // ---- one whole step (:76-100) on a board held in registers --------------------------

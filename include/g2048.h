@@ -33,7 +33,8 @@
  *                    f = (uint32)p;  tile = (f < 3865470567u) ? 2 : 4   [P(2)=0.9]
  *                    the k-th empty cell in row-major order receives the tile.
  *   step spawn uses w[0]; a reset (auto-reset in g2048_step, or g2048_reset)
- *   zeroes the board and spawns with w[1] then w[2].
+ *   zeroes the board and spawns with w[1] then w[2].  w[3] of the step-tag block
+ *   is the policy word of g2048_sample_actions (random / random-legal actions).
  */
 #ifndef G2048_H
 #define G2048_H
@@ -45,7 +46,7 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 1
+#define G2048_ABI_VERSION 2 /* 2: G2048StepArgs.boards_out, data-side entry points */
 
 #define G2048_OK            0
 #define G2048_ERR_INVALID  (-1) /* bad argument (NULL required pointer, bad dtype, ...) */
@@ -71,7 +72,7 @@ extern "C" {
  * highest (:190-192) and — with G2048_FLAG_AUTO_RESET — reset (:102-111).
  */
 typedef struct G2048StepArgs {
-  uint8_t*        boards;          /* [n*16] in/out                                        */
+  uint8_t*        boards;          /* [n*16] in/out (in only when boards_out is set)       */
   const uint8_t*  actions;         /* [n]    0..3; only the low 2 bits are read            */
   float*          rewards;         /* [n]    out: merge score, or illegal_move_reward      */
   uint8_t*        dones;           /* [n]    out: terminated (0/1)                         */
@@ -98,6 +99,10 @@ typedef struct G2048StepArgs {
   float           illegal_move_reward; /* set_illegal_move_reward (:61-67), default 0      */
   uint32_t        max_tile_exp;    /* set_max_tile (:69-73) as exponent; 0 = None          */
   uint32_t        flags;           /* G2048_FLAG_*                                         */
+  uint8_t*        boards_out;      /* [n*16] out, nullable: where the boards handed back   */
+                                   /*        to the agent are written; NULL = in place.    */
+                                   /*        Lets a rollout/trajectory buffer slice t+1 be */
+                                   /*        produced from slice t with no copy.           */
 } G2048StepArgs;
 
 int g2048_abi_version(void);
@@ -159,6 +164,75 @@ int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cel
 /* Debug: out[4*i..4*i+3] = philox4x32_10(ctr[4*i..], key) — known-answer tests. */
 int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* out,
                  uint64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Either side of the step: the random policies that drive it and the        */
+/* transition data it produces (reference: train.py, training_data.py).      */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Uniform-random policy on the device.  legal_mask NULL: action uniform in
+ * {0,1,2,3} (train.py:119 `random.randint(0, 3)`, the benchmark's random
+ * actions).  legal_mask given: uniform among the set bits of legal_mask[i] (all
+ * four when the mask is 0) — the random-legal policy of BASELINE config 4.
+ * action = the k-th set bit, k = hi32(w[3] * popcount), w = the step-tag draw
+ * words of (seed, env id, step_index) (the same block g2048_step uses w[0] of).
+ */
+int g2048_sample_actions(const uint8_t* legal_mask, uint8_t* actions, uint64_t n,
+                         uint64_t env_id_base, uint64_t seed, uint64_t step_index,
+                         void* stream);
+
+/*
+ * One board symmetry applied to n transitions: training_data.hflip
+ * (training_data.py:257-272: columns reversed, actions 1<->3) when hflip != 0,
+ * then training_data.rotate(k) (:274-279: np.rot90(k, axes=(2,1)), action + k
+ * mod 4).  next_in/next_out and actions_in/actions_out are nullable pairs; out
+ * may alias in.
+ */
+int g2048_symmetry(const uint8_t* boards_in, uint8_t* boards_out,
+                   const uint8_t* next_in, uint8_t* next_out,
+                   const uint8_t* actions_in, uint8_t* actions_out, uint64_t n,
+                   int hflip, int k, void* stream);
+
+/*
+ * training_data.augment (training_data.py:281-299): the 8 symmetric copies of n
+ * transitions, laid out as the reference's merge order [X, H, R1 X, R1 H, R2 X,
+ * R2 H, R3 X, R3 H] (H = hflip, Rk = rotate(k)): copy s = 2k+h occupies rows
+ * [s*n, (s+1)*n) of every output ([8n*16] boards, [8n] actions/rewards/dones).
+ */
+int g2048_augment(const uint8_t* boards, const uint8_t* next_boards,
+                  const uint8_t* actions, const float* rewards, const uint8_t* dones,
+                  uint64_t n, uint8_t* boards_out, uint8_t* next_boards_out,
+                  uint8_t* actions_out, float* rewards_out, uint8_t* dones_out,
+                  void* stream);
+
+/*
+ * training_data.get_discounted_return (training_data.py:104-124) over n rows in
+ * game order: G[i] = r[i] if dones[i] or i == n-1, else r[i] + gamma * G[i+1],
+ * evaluated in float64 in the reference's order (no fused multiply-add), one
+ * thread per episode segment.
+ */
+int g2048_discounted_return(const float* rewards, const uint8_t* dones,
+                            double* returns, uint64_t n, double gamma, void* stream);
+
+/*
+ * The reference's transition CSV (training_data.export_csv / import_csv,
+ * training_data.py:188-248), HOST buffers: 16 board tile VALUES, action, reward
+ * ("%f"), 16 next-board values, done, optionally the discounted return; header
+ * "1-1,...,4-4,action,reward,next 1-1,...,next 4-4,done[,return]".  Boards are
+ * exponents on our side and tile values in the file.  export writes the header
+ * unless append != 0.  rows() counts data rows; import fills caller buffers of
+ * n_rows entries (returns nullable) and fails on cells that are not 0 or a
+ * power of two.
+ */
+int g2048_csv_export(const char* path, const uint8_t* boards, const uint8_t* actions,
+                     const double* rewards, const uint8_t* next_boards,
+                     const uint8_t* dones, const double* returns, uint64_t n,
+                     int append);
+int g2048_csv_rows(const char* path, uint64_t* n_rows, int* has_returns);
+int g2048_csv_import(const char* path, uint8_t* boards, uint8_t* actions,
+                     double* rewards, uint8_t* next_boards, uint8_t* dones,
+                     double* returns, uint64_t n_rows);
 
 /* ------------------------------------------------------------------------- */
 /* Stateful host-buffer API: what a non-CUDA host (the reference's Python, a  */

@@ -155,6 +155,10 @@ static void reset_board(uint8_t b[16], const uint32_t w[4]) {     /* :102-111 */
 /* ---- step (:76-100) + SB3 DummyVecEnv same-step auto-reset ----------------- */
 static void step_one(const G2048StepArgs* a, uint64_t i) {
   uint8_t* b = a->boards + 16 * i;
+  if (a->boards_out && a->boards_out != a->boards) {              /* out-of-place step */
+    memcpy(a->boards_out + 16 * i, b, 16);
+    b = a->boards_out + 16 * i;
+  }
   int action = a->actions[i] & 3;
   uint32_t w[4];
   if (a->forced_draws) memcpy(w, a->forced_draws + 4 * i, sizeof w);
@@ -307,3 +311,87 @@ uint32_t g2048_oracle_shift(const uint8_t row[4], uint8_t out[4]) {
   return shift_line(row, out);
 }
 
+
+/* ---- the random policies that drive the step (train.py:119 random.randint(0, 3); ------------
+ *      BASELINE config 4's random-legal policy): k-th allowed action, k from draw word 3 ---- */
+int g2048_oracle_sample_actions(const uint8_t* legal_mask, uint8_t* actions, uint64_t n,
+                                uint64_t env_id_base, uint64_t seed, uint64_t step_index) {
+  if (!actions) return G2048_ERR_INVALID;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t w[4];
+    draw_words(seed, env_id_base + i, step_index, 0, w);
+    int allowed[4], cnt = 0;
+    for (int d = 0; d < 4; ++d)
+      if (!legal_mask || (legal_mask[i] & 15) == 0 || ((legal_mask[i] >> d) & 1)) allowed[cnt++] = d;
+    uint32_t k = (uint32_t)(((uint64_t)w[3] * (uint64_t)cnt) >> 32);
+    actions[i] = (uint8_t)allowed[k];
+  }
+  return G2048_OK;
+}
+
+/* ---- training_data.py symmetries, following the numpy calls cell by cell ------------------- */
+/* hflip (:257-272): np.flip(x, 2): new[r][c] = old[r][3-c]; actions 1 <-> 3 */
+static void hflip_board(const uint8_t* in, uint8_t* out) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out[4 * r + c] = in[4 * r + (3 - c)];
+}
+/* rotate(1) (:274-279): np.rot90(x, k=1, axes=(2,1)).  rot90 with axes (a,b) is
+ * flip(transpose) for k=1: result = transpose(flip(m, axis=b)); for one board with
+ * (a,b) = (cols, rows): new[r][c] = old[3-c][r]. */
+static void rot1_board(const uint8_t* in, uint8_t* out) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out[4 * r + c] = in[4 * (3 - c) + r];
+}
+static void sym_board(const uint8_t* in, uint8_t* out, int hflip, int k) {
+  uint8_t t[16], u[16];
+  memcpy(t, in, 16);
+  if (hflip) { hflip_board(t, u); memcpy(t, u, 16); }
+  for (int i = 0; i < k; ++i) { rot1_board(t, u); memcpy(t, u, 16); }
+  memcpy(out, t, 16);
+}
+static uint8_t sym_action(uint8_t a, int hflip, int k) {
+  if (hflip) { if (a == 1) a = 3; else if (a == 3) a = 1; }           /* :262-268 */
+  return (uint8_t)((a + k) % 4);                                      /* :277 */
+}
+int g2048_oracle_symmetry(const uint8_t* boards_in, uint8_t* boards_out, const uint8_t* actions_in,
+                          uint8_t* actions_out, uint64_t n, int hflip, int k) {
+  for (uint64_t i = 0; i < n; ++i) {
+    sym_board(boards_in + 16 * i, boards_out + 16 * i, hflip, k);
+    if (actions_in && actions_out) actions_out[i] = sym_action(actions_in[i], hflip, k);
+  }
+  return G2048_OK;
+}
+/* augment (:281-299): [X, H] then rotations 1..3 of those 2n rows appended */
+int g2048_oracle_augment(const uint8_t* boards, const uint8_t* next_boards, const uint8_t* actions,
+                         const float* rewards, const uint8_t* dones, uint64_t n, uint8_t* boards_out,
+                         uint8_t* next_out, uint8_t* actions_out, float* rewards_out, uint8_t* dones_out) {
+  for (int k = 0; k < 4; ++k)
+    for (int h = 0; h < 2; ++h)
+      for (uint64_t i = 0; i < n; ++i) {
+        uint64_t o = (uint64_t)(2 * k + h) * n + i;
+        sym_board(boards + 16 * i, boards_out + 16 * o, h, k);
+        sym_board(next_boards + 16 * i, next_out + 16 * o, h, k);
+        actions_out[o] = sym_action(actions[i], h, k);
+        rewards_out[o] = rewards[i];
+        dones_out[o] = dones[i];
+      }
+  return G2048_OK;
+}
+/* get_discounted_return (:104-124): one reverse pass, `previous` cleared at done rows */
+int g2048_oracle_discounted_return(const float* rewards, const uint8_t* dones, double* returns,
+                                   uint64_t n, double gamma) {
+  int have_prev = 0;
+  volatile double previous = 0.0;          /* volatile: keep the two roundings (no fma) */
+  for (uint64_t i = n; i-- > 0;) {
+    double smoothed = (double)rewards[i];
+    if (dones[i]) have_prev = 0;
+    if (have_prev && previous != 0.0) {
+      volatile double prod = gamma * previous;
+      smoothed += prod;
+    }
+    returns[i] = smoothed;
+    previous = smoothed;
+    have_prev = 1;
+  }
+  return G2048_OK;
+}

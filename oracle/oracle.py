@@ -22,7 +22,7 @@ class StepArgs(C.Structure):
         ("n", C.c_uint64), ("env_id_base", C.c_uint64), ("seed", C.c_uint64),
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("boards_out", C.c_void_p),
     ]
 
 
@@ -169,3 +169,46 @@ def shift(row_exps):
     o = (C.c_uint8 * 4)()
     s = lib().g2048_oracle_shift(r, o)
     return list(o), int(s)
+
+
+def sample_actions(legal_mask, n, env_id_base, seed, step_index):
+    m = None if legal_mask is None else np.ascontiguousarray(legal_mask, dtype=np.uint8)
+    out = np.zeros(n, np.uint8)
+    rc = lib().g2048_oracle_sample_actions(_p(m), _p(out), C.c_uint64(n), C.c_uint64(env_id_base),
+                                           C.c_uint64(seed), C.c_uint64(step_index))
+    assert rc == 0
+    return out
+
+
+def symmetry(boards, actions, hflip, k):
+    b = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 16)
+    a = None if actions is None else np.ascontiguousarray(actions, dtype=np.uint8)
+    ob = np.empty_like(b)
+    oa = None if a is None else np.empty_like(a)
+    rc = lib().g2048_oracle_symmetry(_p(b), _p(ob), _p(a), _p(oa), C.c_uint64(len(b)), C.c_int(hflip), C.c_int(k))
+    assert rc == 0
+    return ob, oa
+
+
+def augment(boards, next_boards, actions, rewards, dones):
+    b = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 16)
+    nb = np.ascontiguousarray(next_boards, dtype=np.uint8).reshape(-1, 16)
+    a = np.ascontiguousarray(actions, dtype=np.uint8)
+    r = np.ascontiguousarray(rewards, dtype=np.float32)
+    d = np.ascontiguousarray(dones, dtype=np.uint8)
+    n = len(b)
+    o = dict(boards=np.empty((8 * n, 16), np.uint8), next_boards=np.empty((8 * n, 16), np.uint8),
+             actions=np.empty(8 * n, np.uint8), rewards=np.empty(8 * n, np.float32), dones=np.empty(8 * n, np.uint8))
+    rc = lib().g2048_oracle_augment(_p(b), _p(nb), _p(a), _p(r), _p(d), C.c_uint64(n), _p(o["boards"]),
+                                    _p(o["next_boards"]), _p(o["actions"]), _p(o["rewards"]), _p(o["dones"]))
+    assert rc == 0
+    return o
+
+
+def discounted_return(rewards, dones, gamma=0.9):
+    r = np.ascontiguousarray(rewards, dtype=np.float32)
+    d = np.ascontiguousarray(dones, dtype=np.uint8)
+    out = np.zeros(len(r), np.float64)
+    rc = lib().g2048_oracle_discounted_return(_p(r), _p(d), _p(out), C.c_uint64(len(r)), C.c_double(gamma))
+    assert rc == 0
+    return out

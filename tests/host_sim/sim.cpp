@@ -122,3 +122,29 @@ extern "C" int sim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_
   }
   return 0;
 }
+
+extern "C" int sim_symmetry(const uint8_t* in, uint8_t* out, const uint8_t* act_in, uint8_t* act_out, uint64_t n,
+                            int hflip, int k) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r[4];
+    load(in + 16 * i, r);
+    if (hflip) board_hflip(r[0], r[1], r[2], r[3]);
+    for (int q = 0; q < k; ++q) board_rot1(r[0], r[1], r[2], r[3]);
+    store(out + 16 * i, r);
+    if (act_in && act_out) {
+      uint32_t a = act_in[i] & 3u;
+      if (hflip) a = action_hflip(a);
+      act_out[i] = (uint8_t)((a + (uint32_t)k) & 3u);
+    }
+  }
+  return 0;
+}
+
+extern "C" int sim_sample_actions(const uint8_t* mask, uint8_t* actions, uint64_t n, uint64_t base, uint64_t seed,
+                                  uint64_t step_index) {
+  for (uint64_t i = 0; i < n; ++i) {
+    Words w = draw_words(seed, base + i, step_index, 0);
+    actions[i] = (uint8_t)pick_action(mask ? mask[i] : 15u, w.w3);
+  }
+  return 0;
+}

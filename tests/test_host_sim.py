@@ -46,3 +46,40 @@ def test_rollout_vs_oracle_legal_midgame():
 def test_rollout_vs_oracle_max_tile_noreset():
     pc.check_against_oracle(SimOps, n=1024, steps=300, seed=456, policy="legal", max_tile_exp=6,
                             auto_reset=False)
+
+
+def test_symmetries_match_reference_and_oracle():
+    """training_data.hflip / rotate PRMT networks vs the reference fixtures and the oracle."""
+    import ctypes as C
+    import numpy as np
+    from backends import sim_lib, _p
+    from conftest import load_golden
+    from oracle import oracle
+    gold = load_golden("transitions.npz")
+    x, y = gold["syn/in_x"], gold["syn/in_y"]
+    for tag, h, k in (("hflip", 1, 0), ("rot1", 0, 1), ("rot2", 0, 2), ("rot3", 0, 3), ("hflip_rot3", 1, 3)):
+        ob, oa = np.empty_like(x), np.empty_like(y)
+        sim_lib().sim_symmetry(_p(x), _p(ob), _p(y), _p(oa), C.c_uint64(len(x)), C.c_int(h), C.c_int(k))
+        assert np.array_equal(ob, gold["syn/%s_x" % tag]) and np.array_equal(oa, gold["syn/%s_y" % tag]), tag
+    rng = np.random.default_rng(5)
+    b = rng.integers(0, 19, (5000, 16)).astype(np.uint8)
+    a = rng.integers(0, 4, 5000).astype(np.uint8)
+    for h in (0, 1):
+        for k in range(4):
+            ob, oa = np.empty_like(b), np.empty_like(a)
+            sim_lib().sim_symmetry(_p(b), _p(ob), _p(a), _p(oa), C.c_uint64(len(b)), C.c_int(h), C.c_int(k))
+            rb, ra = oracle.symmetry(b, a, h, k)
+            assert np.array_equal(ob, rb) and np.array_equal(oa, ra), (h, k)
+
+
+def test_sample_actions_matches_oracle():
+    import ctypes as C
+    import numpy as np
+    from backends import sim_lib, _p
+    from oracle import oracle
+    n = 50000
+    masks = np.random.default_rng(9).integers(0, 16, n).astype(np.uint8)
+    for m in (masks, None):
+        out = np.zeros(n, np.uint8)
+        sim_lib().sim_sample_actions(_p(m), _p(out), C.c_uint64(n), C.c_uint64(123), C.c_uint64(42), C.c_uint64(17))
+        assert np.array_equal(out, oracle.sample_actions(m, n, 123, 42, 17))
