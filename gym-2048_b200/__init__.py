@@ -6,6 +6,8 @@ Public surface:
   Game2048Env       single-env class with the reference's gymnasium + game API (env.py)
   Game2048VecEnv    Stable-Baselines3-style VecEnv adapter over BatchedGame2048 (vec_env.py)
   Transitions / TransitionRecorder  the reference's transition table + CSV schema on the GPU (transitions.py)
+  RolloutCollector  on-device PPO rollout loop + compact rollout buffer + GAE kernel (rollout.py)
+  evaluate_model    the reference's train.evaluate_model with all episodes at once (evaluate.py)
   stack, IllegalMove  as in the reference module
 The CUDA extension is built in-tree by `_lib.build()` (nvcc, sm_100a); nothing here has a
 CPU fallback.
@@ -17,8 +19,12 @@ from .stats import EpisodeStats
 from .env import Game2048Env, IllegalMove, register, stack
 from .vec_env import Game2048VecEnv
 from .transitions import TransitionRecorder, Transitions
+from .rollout import RolloutCollector, gae_reference
+from .evaluate import evaluate_model, report_evaluation_results
+from .policy import ResNetActorCritic
 
 __all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Game2048VecEnv", "IllegalMove",
            "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS",
-           "Transitions", "TransitionRecorder"]
+           "Transitions", "TransitionRecorder", "RolloutCollector", "gae_reference", "evaluate_model",
+           "report_evaluation_results", "ResNetActorCritic"]
 __version__ = "0.1.0"

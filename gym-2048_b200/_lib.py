@@ -26,7 +26,7 @@ EXPORTS = [
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
-    "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return",
+    "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return", "g2048_gae",
     "g2048_csv_export", "g2048_csv_rows", "g2048_csv_import",
 ]
 
@@ -134,6 +134,7 @@ def lib():
     L.g2048_symmetry.argtypes = [vp, vp, vp, vp, vp, vp, u64, C.c_int, C.c_int, vp]
     L.g2048_augment.argtypes = [vp] * 5 + [u64] + [vp] * 6
     L.g2048_discounted_return.argtypes = [vp, vp, vp, u64, C.c_double, vp]
+    L.g2048_gae.argtypes = [vp] * 7 + [u64, u64, C.c_double, C.c_double, vp]
     L.g2048_csv_export.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, u64, C.c_int]
     L.g2048_csv_rows.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_int)]
     L.g2048_csv_import.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, u64]

@@ -97,6 +97,30 @@ g2048_discounted_return_kernel(const float* rewards, const uint8_t* dones, doubl
   }
 }
 
+// GAE(lambda) over a time-major [T,n] rollout (SB3 RolloutBuffer.compute_returns_and_advantage).
+// Thread i owns env i and walks t = T-1..0; at every t the warp reads/writes consecutive floats.
+__global__ void __launch_bounds__(kThreads)
+g2048_gae_kernel(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+                 const uint8_t* last_dones, float* advantages, float* returns, uint64_t T, uint64_t n, float gamma,
+                 float gl) {                       // gl = float(gamma * gae_lambda), product taken in double
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    float next_value = last_values[i];
+    float next_non_terminal = last_dones[i] ? 0.f : 1.f;
+    float gae = 0.f;
+    for (uint64_t t = T; t-- > 0;) {
+      const uint64_t o = t * n + i;
+      const float v = values[o];
+      const float delta = __fsub_rn(__fadd_rn(rewards[o], __fmul_rn(__fmul_rn(gamma, next_value), next_non_terminal)), v);
+      gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, next_non_terminal), gae));
+      advantages[o] = gae;
+      returns[o] = __fadd_rn(gae, v);
+      next_value = v;
+      next_non_terminal = episode_starts[o] ? 0.f : 1.f;
+    }
+  }
+}
+
 }  // namespace g2048
 
 using namespace g2048;
@@ -150,6 +174,18 @@ int g2048_discounted_return(const float* rewards, const uint8_t* dones, double* 
   g2048_discounted_return_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       rewards, dones, returns, n, gamma);
   return launch_check("g2048_discounted_return_kernel");
+}
+
+int g2048_gae(const float* rewards, const float* values, const uint8_t* episode_starts, const float* last_values,
+              const uint8_t* last_dones, float* advantages, float* returns, uint64_t T, uint64_t n, double gamma,
+              double gae_lambda, void* stream) {
+  if (n == 0 || T == 0) return G2048_OK;
+  if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns)
+    return fail(G2048_ERR_INVALID, "g2048_gae: NULL pointer");
+  g2048_gae_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      rewards, values, episode_starts, last_values, last_dones, advantages, returns, T, n, (float)gamma,
+      (float)(gamma * gae_lambda));
+  return launch_check("g2048_gae_kernel");
 }
 
 }  // extern "C"

@@ -216,6 +216,22 @@ int g2048_discounted_return(const float* rewards, const uint8_t* dones,
                             double* returns, uint64_t n, double gamma, void* stream);
 
 /*
+ * Generalised advantage estimation over a [T,n] rollout (time-major, env fastest), the
+ * computation SB3's RolloutBuffer.compute_returns_and_advantage runs after the rollout of
+ * ppo_train.py:138-183 (third-party; restated from its published algorithm):
+ *   for t = T-1..0: nn = 1 - (t == T-1 ? last_dones : episode_starts[t+1]);
+ *                   nv = (t == T-1 ? last_values : values[t+1]);
+ *                   delta = r[t] + gamma*nv*nn - v[t];  A[t] = delta + gamma*lambda*nn*A[t+1];
+ *   returns = A + values.   float32 with gamma and gamma*lambda (product in double) rounded
+ *   to float32 first, each product/sum rounded separately (no fma): the result equals the
+ *   numpy float32 expression evaluated op by op.  One thread per env.
+ */
+int g2048_gae(const float* rewards, const float* values, const uint8_t* episode_starts,
+              const float* last_values, const uint8_t* last_dones, float* advantages,
+              float* returns, uint64_t T, uint64_t n, double gamma, double gae_lambda,
+              void* stream);
+
+/*
  * The reference's transition CSV (training_data.export_csv / import_csv,
  * training_data.py:188-248), HOST buffers: 16 board tile VALUES, action, reward
  * ("%f"), 16 next-board values, done, optionally the discounted return; header
