@@ -88,8 +88,11 @@ struct StepParams {
   uint32_t* final_len;
   const uint4* forced_draws;
   const uint64_t* step_counter;
-  uint64_t n, env_id_base, seed, step_index;
+  uint32_t n;                   // < 2^32 - 256 (checked by the host)
+  uint32_t env_lo;              // low half of the env id of board 0; the launch never crosses 2^32
+  uint32_t env_hi;              // high half (counter word 3, tag bit clear), the same for every board
   RoundKeys rk;                 // Philox round keys of `seed`
+  PhiloxHead head;              // launch-uniform part of Philox rounds 0-1 for (seed, step_index, env_hi)
   float illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t flags;
@@ -104,21 +107,21 @@ __device__ __forceinline__ const Board4* make_reset_lut(Board4* s_lut) {
   return s_lut;
 }
 
-// One board through Game2048Env.step and out to memory.
+// One board, already rotated into its move frame (a,b,c,d), through Game2048Env.step and out to memory.
 template <bool EXTRAS>
-__device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint4 bd,
-                                               uint32_t action, uint64_t step_index, bool auto_reset) {
+__device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
+                                               uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
+                                               const PhiloxHead& head, bool auto_reset) {
   Words w;
   if (EXTRAS && p.forced_draws) {
     const uint4 f = p.forced_draws[i];
     w = Words{f.x, f.y, f.z, f.w};
   } else {
-    const uint64_t env = p.env_id_base + i;
-    w = philox4x32_10_rk((uint32_t)step_index, (uint32_t)(step_index >> 32), (uint32_t)env,
-                         (uint32_t)(env >> 32) & 0x7FFFFFFFu, p.rk);
+    w = philox4x32_10_head(p.env_lo + i, head, p.rk);
   }
-  const StepOut o = step_board(lut, bd.x, bd.y, bd.z, bd.w, action & 3u, w, p.max_tile_exp,
-                               EXTRAS && p.highest_exp != nullptr, auto_reset);
+  uint4 bd;
+  const StepOut o = step_oriented(lut, a, b, c, d, so, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr,
+                                  auto_reset, bd.x, bd.y, bd.z, bd.w);
   p.boards_out[i] = bd;
   p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
   p.dones[i] = o.done ? 1 : 0;
@@ -150,36 +153,37 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
   const Board4* lut = make_reset_lut(s_lut);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
-  const uint32_t n = (uint32_t)p.n, stride = gridDim.x * kThreads;     // n < 2^32 (checked by the host)
+  const uint32_t n = p.n, stride = gridDim.x * kThreads;
   uint32_t i = blockIdx.x * kThreads + threadIdx.x;
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
   if (i >= n) return;
-  const uint64_t step_index = p.step_counter ? *p.step_counter : p.step_index;
-#if !G2048_PERSISTENT
-  step_and_store<EXTRAS>(p, lut, i, p.boards[i], p.actions[i], step_index, auto_reset);
-#elif !G2048_PREFETCH
-  for (; i < n; i += stride) {
-    step_and_store<EXTRAS>(p, lut, i, p.boards[i], p.actions[i], step_index, auto_reset);
-    if (i + stride <= i) break;
-  }
-#else
-  // Grid-stride loop, software-pipelined one board ahead.  (Unrolling by two to avoid the
-  // register copies was measured slower: the doubled body no longer fits the L0 I-cache.)
+  PhiloxHead head = p.head;
+  if (p.step_counter) head = make_philox_head(*p.step_counter, p.env_hi, p.rk);   // device-side step index
+  // Grid-stride loop, software-pipelined one board ahead.  orient() consumes the loaded board
+  // right away, so the next board is prefetched into the same registers (no rotation copies)
+  // a whole iteration before it is used.  (Unrolling by two was measured slower: the doubled
+  // body no longer fits the L0 instruction cache; so were two boards per thread.)
   uint4 bd = p.boards[i];
   uint32_t action = p.actions[i];
   while (true) {
     const uint32_t i_next = i + stride;
-    const bool more = i_next < n && i_next > i;
-    uint4 bd_next;
-    uint32_t action_next = 0;
-    if (more) { bd_next = p.boards[i_next]; action_next = p.actions[i_next]; }
-    step_and_store<EXTRAS>(p, lut, i, bd, action, step_index, auto_reset);
-    if (!more) break;
-    i = i_next; bd = bd_next; action = action_next;
-  }
+    const bool more = G2048_PERSISTENT && i_next < n && i_next > i;
+    const uint32_t act = action & 3u;
+    uint32_t a, b, c, d;
+    orient(kOrientIn[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+    const Sel4 so = kOrientOut[act];
+#if G2048_PREFETCH
+    if (more) { bd = p.boards[i_next]; action = p.actions[i_next]; }
 #endif
+    step_and_store<EXTRAS>(p, lut, i, a, b, c, d, so, head, auto_reset);
+    if (!more) break;
+#if !G2048_PREFETCH
+    bd = p.boards[i_next]; action = p.actions[i_next];
+#endif
+    i = i_next;
+  }
 }
 
 __global__ void g2048_bump_counter_kernel(uint64_t* counter) { *counter += 1ull; }
@@ -363,17 +367,20 @@ extern "C" {
 int g2048_abi_version(void) { return G2048_ABI_VERSION; }
 const char* g2048_last_error(void) { return g_err; }
 
-int g2048_step(const G2048StepArgs* a, void* stream) {
-  if (!a) return fail(G2048_ERR_INVALID, "g2048_step: args is NULL");
-  if (a->n == 0) return G2048_OK;
-  if (!a->boards || !a->actions || !a->rewards || !a->dones)
-    return fail(G2048_ERR_INVALID, "g2048_step: boards, actions, rewards and dones are required");
-  if (!aligned16(a->boards) || !aligned16(a->boards_out) || !aligned16(a->terminal_boards) ||
-      !aligned16(a->forced_draws))
-    return fail(G2048_ERR_ALIGN,
-                "g2048_step: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned");
-  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
-  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
+// The boards [lo, lo+m) of a call as a call of their own (every per-board pointer advanced).
+static G2048StepArgs slice_args(const G2048StepArgs& a, uint64_t lo, uint64_t m) {
+  G2048StepArgs s = a;
+  auto adv = [lo](auto*& ptr, uint64_t elems_per_board) { if (ptr) ptr += lo * elems_per_board; };
+  adv(s.boards, 16); adv(s.boards_out, 16); adv(s.actions, 1); adv(s.rewards, 1); adv(s.dones, 1);
+  adv(s.illegal, 1); adv(s.highest_exp, 1); adv(s.legal_mask, 1); adv(s.terminal_boards, 16);
+  adv(s.ep_score, 1); adv(s.ep_len, 1); adv(s.final_score, 1); adv(s.final_len, 1); adv(s.forced_draws, 4);
+  s.n = m;
+  s.env_id_base = a.env_id_base + lo;
+  return s;
+}
+
+// One launch; the env ids of the call do not cross a multiple of 2^32.
+static int launch_step(const G2048StepArgs* a, cudaStream_t s) {
   StepParams p;
   p.boards = reinterpret_cast<const uint4*>(a->boards);
   p.boards_out = reinterpret_cast<uint4*>(a->boards_out ? a->boards_out : a->boards);
@@ -390,17 +397,16 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   p.final_len = a->final_len;
   p.forced_draws = reinterpret_cast<const uint4*>(a->forced_draws);
   p.step_counter = a->step_counter;
-  p.n = a->n;
-  p.env_id_base = a->env_id_base;
-  p.seed = a->seed;
+  p.n = (uint32_t)a->n;
+  p.env_lo = (uint32_t)a->env_id_base;
+  p.env_hi = (uint32_t)(a->env_id_base >> 32) & 0x7FFFFFFFu;
   make_round_keys(a->seed, p.rk);
-  p.step_index = a->step_index;
+  p.head = make_philox_head(a->step_index, p.env_hi, p.rk);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = a->flags;
   const bool extras = a->illegal || a->highest_exp || a->legal_mask || a->terminal_boards || a->ep_score ||
                       a->ep_len || a->final_score || a->final_len || a->forced_draws;
-  const cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
 #if G2048_PERSISTENT
@@ -420,6 +426,33 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<true>, p)
                                 : cudaLaunchKernelEx(&cfg, g2048_step_kernel<false>, p);
   if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_kernel)");
+  return G2048_OK;
+}
+
+int g2048_step(const G2048StepArgs* a, void* stream) {
+  if (!a) return fail(G2048_ERR_INVALID, "g2048_step: args is NULL");
+  if (a->n == 0) return G2048_OK;
+  if (!a->boards || !a->actions || !a->rewards || !a->dones)
+    return fail(G2048_ERR_INVALID, "g2048_step: boards, actions, rewards and dones are required");
+  if (!aligned16(a->boards) || !aligned16(a->boards_out) || !aligned16(a->terminal_boards) ||
+      !aligned16(a->forced_draws))
+    return fail(G2048_ERR_ALIGN,
+                "g2048_step: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned");
+  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
+  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // The kernel treats the high half of the env id as launch-uniform (Philox head): a call whose
+  // ids cross a multiple of 2^32 is issued as two launches.
+  const uint64_t to_boundary = 0x100000000ull - (a->env_id_base & 0xFFFFFFFFull);
+  if (a->n > to_boundary) {
+    const G2048StepArgs first = slice_args(*a, 0, to_boundary), second = slice_args(*a, to_boundary, a->n - to_boundary);
+    int rc = launch_step(&first, s);
+    if (rc == G2048_OK) rc = launch_step(&second, s);
+    if (rc != G2048_OK) return rc;
+  } else {
+    const int rc = launch_step(a, s);
+    if (rc != G2048_OK) return rc;
+  }
   if (a->step_counter) g2048_bump_counter_kernel<<<1, 1, 0, s>>>(a->step_counter);
   return launch_check("g2048_step_kernel");
 }

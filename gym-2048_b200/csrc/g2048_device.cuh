@@ -17,9 +17,11 @@
 // byte-SIMD logic on the CPU box; the product only ever compiles it with nvcc.
 #ifdef G2048_HOST_SIM
 #define G2048_DEV inline
+#define G2048_HD inline
 #define G2048_CONST static const
 #else
 #define G2048_DEV __device__ __forceinline__
+#define G2048_HD __host__ __device__ __forceinline__
 #define G2048_CONST static __constant__      // one copy per translation unit (no relocatable device code)
 #endif
 
@@ -117,12 +119,53 @@ G2048_DEV Words philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
   }
   return Words{c0, c1, c2, c3};
 }
-inline void make_round_keys(uint64_t seed, RoundKeys& rk) {
+G2048_HD void make_round_keys(uint64_t seed, RoundKeys& rk) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   for (int r = 0; r < 10; ++r) {
     rk.k0[r] = k0; rk.k1[r] = k1;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
+}
+
+// Within one launch only counter word 2 (the low half of the env id) differs between boards:
+// c0,c1 = step index and c3 = high half of the env id (| tag) are the same for every board, as
+// long as the launch does not straddle a 2^32 boundary of env ids (the host splits it there).
+// Round 0 then has one varying product (M1 * env_lo) and round 1 one (M0 * c0'); everything else
+// of those two rounds folds into four words computed once per launch:
+//   round 0: c0' = hi(M1*env_lo) ^ A        c1' = lo(M1*env_lo)   c2' = B (uniform)   c3' = C (uniform)
+//   round 1: c0" = c1' ^ E                  c1" = lo(M1*B) (uniform, folded into G)
+//            c2" = hi(M0*c0') ^ F           c3" = lo(M0*c0')
+//   round 2: c0 = hi(M1*c2") ^ G, the rest as usual.
+// Saves 2 of the 20 wide multiplies, a 64-bit add and two logic ops per board.
+struct PhiloxHead { uint32_t A, E, F, G; };
+G2048_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+G2048_HD PhiloxHead make_philox_head(uint64_t idx, uint32_t c3, const RoundKeys& rk) {
+  const uint32_t s_lo = (uint32_t)idx, s_hi = (uint32_t)(idx >> 32);
+  const uint32_t B = mulhi32(0xD2511F53u, s_lo) ^ c3 ^ rk.k1[0];
+  const uint32_t Cw = 0xD2511F53u * s_lo;
+  PhiloxHead h;
+  h.A = s_hi ^ rk.k0[0];
+  h.E = mulhi32(0xCD9E8D57u, B) ^ rk.k0[1];
+  h.F = Cw ^ rk.k1[1];
+  h.G = (0xCD9E8D57u * B) ^ rk.k0[2];
+  return h;
+}
+G2048_DEV Words philox4x32_10_head(uint32_t env_lo, const PhiloxHead& h, const RoundKeys& rk) {
+  const uint32_t c0a = __umulhi(0xCD9E8D57u, env_lo) ^ h.A, c1a = 0xCD9E8D57u * env_lo;     // round 0
+  const uint32_t c0b = c1a ^ h.E;                                                             // round 1
+  const uint32_t c2b = __umulhi(0xD2511F53u, c0a) ^ h.F, c3b = 0xD2511F53u * c0a;
+  uint32_t c0 = __umulhi(0xCD9E8D57u, c2b) ^ h.G, c1 = 0xCD9E8D57u * c2b;                    // round 2
+  uint32_t c2 = __umulhi(0xD2511F53u, c0b) ^ c3b ^ rk.k1[2], c3 = 0xD2511F53u * c0b;
+#pragma unroll
+  for (int r = 3; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk.k0[r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ rk.k1[r];
+    c3 = lo0;
+  }
+  return Words{c0, c1, c2, c3};
 }
 
 // Draw words for (seed, global env id, index, tag) — include/g2048.h "Draw stream".
@@ -367,20 +410,21 @@ struct StepOut {
   uint32_t t0, t1, t2, t3;   // post-spawn board (the terminal board when done)
 };
 
-// On return r0..r3 hold the board handed back to the agent: the post-spawn board, or a
-// fresh reset() board when the episode ended and auto_reset is set (SB3 DummyVecEnv).
-G2048_DEV StepOut step_board(const Board4* lut, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
-                             uint32_t action, const Words& w, uint32_t max_tile_exp, bool want_highest,
-                             bool auto_reset) {
+// The step on a board already rotated into the move frame (a,b,c,d) (see orient); `so` is the
+// inverse rotation.  On return r0..r3 hold the board handed back to the agent: the post-spawn
+// board, or a fresh reset() board when the episode ended and auto_reset is set (SB3 DummyVecEnv).
+// Taking the oriented board lets the step kernel reuse the registers of the loaded board for the
+// next board's prefetch as soon as orient() has consumed them.
+G2048_DEV StepOut step_oriented(const Board4* lut, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
+                                const Words& w, uint32_t max_tile_exp, bool want_highest, bool auto_reset,
+                                uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   StepOut o;
-  uint32_t a, b, c, d;
-  orient(kOrientIn[action], r0, r1, r2, r3, a, b, c, d);
   const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
-  o.score = slide_merge(a, b, c, d);
+  o.score = slide_merge(a, b, c, d);                                                     // :85, :194-241
   // :238-239 — nothing changed => IllegalMove.  An illegal move leaves (a,b,c,d) as they
   // were and scores 0, so the same data path serves both cases; only the spawn is gated.
   o.legal = (((a ^ a0) | (b ^ b0)) | ((c ^ c0) | (d ^ d0))) != 0u;
-  orient(kOrientOut[action], a, b, c, d, r0, r1, r2, r3);
+  orient(so, a, b, c, d, r0, r1, r2, r3);
   const uint32_t n_empty = spawn(r0, r1, r2, r3, w.w0, o.legal ? 0xFFFFFFFFu : 0u);     // :88
   o.highest = 0;
   if (want_highest || max_tile_exp != 0u) o.highest = highest_exp(r0, r1, r2, r3);      // :97
@@ -389,8 +433,17 @@ G2048_DEV StepOut step_board(const Board4* lut, uint32_t& r0, uint32_t& r1, uint
   if (max_tile_exp != 0u) end = end || (o.highest == max_tile_exp);                      // :267
   o.done = end || !o.legal;
   o.t0 = r0; o.t1 = r1; o.t2 = r2; o.t3 = r3;
-  if (auto_reset && o.done) fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);                    // :102-111
+  if (auto_reset && o.done) fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);                // :102-111
   return o;
+}
+
+G2048_DEV StepOut step_board(const Board4* lut, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                             uint32_t action, const Words& w, uint32_t max_tile_exp, bool want_highest,
+                             bool auto_reset) {
+  uint32_t a, b, c, d;
+  orient(kOrientIn[action], r0, r1, r2, r3, a, b, c, d);
+  return step_oriented(lut, a, b, c, d, kOrientOut[action], w, max_tile_exp, want_highest, auto_reset, r0, r1, r2,
+                       r3);
 }
 
 }  // namespace g2048

@@ -148,3 +148,15 @@ extern "C" int sim_sample_actions(const uint8_t* mask, uint8_t* actions, uint64_
   }
   return 0;
 }
+
+extern "C" int sim_philox_head(uint64_t seed, uint64_t idx, const uint64_t* env_ids, uint32_t tag, uint32_t* out, uint64_t n) {
+  RoundKeys rk;
+  make_round_keys(seed, rk);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t c3 = ((uint32_t)(env_ids[i] >> 32) & 0x7FFFFFFFu) | (tag << 31);
+    const PhiloxHead h = make_philox_head(idx, c3, rk);
+    const Words w = philox4x32_10_head((uint32_t)env_ids[i], h, rk);
+    out[4 * i] = w.w0; out[4 * i + 1] = w.w1; out[4 * i + 2] = w.w2; out[4 * i + 3] = w.w3;
+  }
+  return 0;
+}

@@ -154,3 +154,52 @@ def test_full_size_properties_1m():
     # mean P(4) over spawns ~ 0.1
     fours = (b0 == 2).sum().item() / (2 * n)
     assert abs(fours - 0.1) < 0.002
+
+
+def test_batch_crossing_a_2_32_env_id_boundary(ops):
+    """The kernel folds the high half of the env id into a launch-uniform Philox head; a batch
+    whose ids cross a multiple of 2^32 is split into two launches by the library."""
+    pc.check_against_oracle(ops, n=5000, steps=40, seed=3, policy="random", env_id_base=(1 << 32) - 1234)
+    pc.check_against_oracle(ops, n=3000, steps=40, seed=4, policy="legal", env_id_base=(5 << 32) - 1)
+
+
+def test_lean_kernel_crossing_boundary_and_device_step_counter():
+    """Lean outputs (boards, rewards, dones only), ids crossing 2^32, step index kept on the device
+    and the loop replayed as a CUDA graph: same boards as host-indexed stepping and as the oracle."""
+    import torch
+    import gym_2048_b200 as g
+    n, base, T = 4096, (1 << 32) - 777, 24
+    dev = torch.device("cuda", 0)
+    acts = torch.randint(0, 4, (T, n), device=dev, dtype=torch.uint8,
+                         generator=torch.Generator(device=dev).manual_seed(8))
+    ref = oracle.OracleBatch(n, seed=9, env_id_base=base)
+    ref.reset()
+    host = g.BatchedGame2048(n, seed=9, env_id_base=base, outputs=())
+    host.reset()
+    for t in range(T):
+        ref.step(acts[t].cpu().numpy())
+        host.step(acts[t])
+    assert np.array_equal(host.boards.cpu().numpy(), ref.boards)
+    # device-side counter, first 8 steps eagerly, then 2 replays of an 8-step graph
+    gm = g.BatchedGame2048(n, seed=9, env_id_base=base, outputs=())
+    gm.reset()
+    gm.use_device_step_counter(True)
+    for t in range(8):
+        gm.step(acts[t])
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    staged = acts[8:16].clone()
+    with torch.cuda.stream(stream):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for t in range(8):
+                gm.step(staged[t])
+    # capture does not execute: the counter still says 8
+    graph.replay()
+    torch.cuda.synchronize()
+    staged.copy_(acts[16:24])
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(gm.boards.cpu().numpy(), ref.boards)
+    gm.use_device_step_counter(False)
+    assert gm.step_index == T
