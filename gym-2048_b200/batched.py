@@ -255,14 +255,14 @@ class BatchedGame2048:
         return out
 
     def use_device_step_counter(self, enable=True):
-        """Keep the step index in device memory (bumped by a 1-thread kernel after each step) so
+        """Keep the step index in device memory (advanced by the step kernel itself as it ends) so
         a loop of step() calls can be captured once in a CUDA graph and replayed: with the
         default host-side index every replay would reuse the captured step's draws."""
         if enable:
-            self._step_counter = torch.tensor([self.step_index], dtype=torch.int64, device=self.device)
+            self._step_counter = torch.tensor([self.step_index, 0], dtype=torch.int64, device=self.device)
         else:
             if self._step_counter is not None:
-                self.step_index = int(self._step_counter.item())
+                self.step_index = int(self._step_counter[0].item())
             self._step_counter = None
 
     # -- move / status -----------------------------------------------------------------
@@ -329,7 +329,7 @@ class BatchedGame2048:
     # -- checkpoint / resume -------------------------------------------------------------
     def state_dict(self):
         if self._step_counter is not None:
-            self.step_index = int(self._step_counter.item())
+            self.step_index = int(self._step_counter[0].item())
         sd = dict(boards=self.boards.clone(), seed=self.seed, step_index=self.step_index,
                   reset_index=self.reset_index, env_id_base=self.env_id_base)
         if self.ep_score is not None:
@@ -341,7 +341,7 @@ class BatchedGame2048:
         self.seed, self.step_index, self.reset_index = int(sd["seed"]), int(sd["step_index"]), int(sd["reset_index"])
         self.env_id_base = int(sd["env_id_base"])
         if self._step_counter is not None:
-            self._step_counter.fill_(self.step_index)
+            self._step_counter[0] = self.step_index
         if self.ep_score is not None and "ep_score" in sd:
             self.ep_score.copy_(sd["ep_score"])
             self.ep_len.copy_(sd["ep_len"])

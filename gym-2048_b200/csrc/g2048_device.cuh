@@ -71,7 +71,12 @@ __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(kOne), "r"(y));
   return d;
 }
-template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
+#ifndef G2048_SHR_ALU         // 1: constant right shifts as SHF (ALU pipe) instead of IMAD.HI (FMA-heavy, quarter rate)
+#define G2048_SHR_ALU 0
+#endif
+template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) {
+  return G2048_SHR_ALU ? (x >> S) : __umulhi(x, 1u << (32 - S));
+}
 template <int S> __device__ __forceinline__ uint32_t shl(uint32_t x) { return x * (1u << S); }
 // hi32(a * b) + c in one IMAD.HI
 __device__ __forceinline__ uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) {

@@ -88,10 +88,11 @@ typedef struct G2048StepArgs {
   uint32_t*       final_len;       /* [n]    out, nullable: episode length, where done     */
   const uint32_t* forced_draws;    /* [n*4]  nullable: words used INSTEAD of the Philox    */
                                    /*        output w[0..3] (fixture / CSV parity)         */
-  uint64_t*       step_counter;    /* nullable device uint64: when set the step index is   */
-                                   /*        read from *step_counter instead of step_index */
-                                   /*        and a follow-up kernel on the same stream     */
-                                   /*        increments it (CUDA-graph capture friendly)   */
+  uint64_t*       step_counter;    /* nullable device uint64[2]: when set the step index is */
+                                   /*        read from step_counter[0] instead of step_index */
+                                   /*        and the launch itself advances it when it ends  */
+                                   /*        (CUDA-graph replay); step_counter[1] is scratch */
+                                   /*        of the library and must be 0 before the 1st use */
   uint64_t        n;               /* boards in this call                                  */
   uint64_t        env_id_base;     /* global env id of element 0                           */
   uint64_t        seed;            /* Philox key                                           */
