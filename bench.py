@@ -124,44 +124,39 @@ def host_cpu_model():
 
 
 def run_reference(args):
+    """`--impl reference`: the UNMODIFIED reference step() on all host cores.  A bench "step" is a
+    bounded sample of the workload: `per` step() calls on each of `cores` single-env processes.  All
+    W + K bench steps of a worker run inside ONE process-pool call (no per-step IPC), and `per` shrinks
+    as K grows, so the whole run takes seconds to a few minutes whatever K the driver passes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
     config = workload_config(args, world=args.gpus)
+    K, W = max(args.steps, 1), max(args.warmup, 0)
     if reference_available():
         kind = "reference"
-        per_step = args.ref_steps_per_proc
-        pool = mp.get_context("spawn").Pool(cores)
-        try:
-            for _ in range(args.warmup):
-                time_reference(cores, max(per_step // 4, 50), pool=pool)
-            t0 = time.perf_counter()
-            total = 0
-            for _ in range(args.steps):
-                v, _ = time_reference(cores, per_step, pool=pool)
-                total += cores * per_step
-            dt = time.perf_counter() - t0
-        finally:
-            pool.close()
-            pool.join()
-        value = total / dt
-        sample = "%d processes x 1 reference env x %d step() calls per bench step, uniform-random actions, " \
-                 "reset() on terminated" % (cores, per_step)
+        budget_calls = 400000                                    # per process: ~20 s at ~20k step()/s
+        per = max(1, min(args.ref_steps_per_proc, budget_calls // (K + W)))
+        value, wall = time_reference(cores, per * K, warm=per * W + 50)
+        dt = cores * per * K / value
+        sample = "%d processes x 1 unmodified reference env x %d step() calls per bench step, uniform-random " \
+                 "actions, reset() on terminated" % (cores, per)
     else:
         kind = "port"
         n = 1 << 18
-        for _ in range(args.warmup):
+        for _ in range(min(W, 3)):
             time_port(n, 2, cores)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        reps = min(K, 64)
+        for _ in range(reps):
             time_port(n, 4, cores)
-        dt = time.perf_counter() - t0
-        value = n * 4 * args.steps / dt
+        dt = (time.perf_counter() - t0) * K / reps
+        value = n * 4 * K / dt
         sample = "C oracle port, %d threads, %d envs x 4 steps per bench step" % (cores, n)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
@@ -397,11 +392,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        args.steps = 4 if args.steps is None else args.steps
-        args.warmup = 1 if args.warmup is None else args.warmup
-        # keep the whole run bounded whatever K the driver passes
-        budget_calls = 120000                      # ~6 s per process at ~20k steps/s
-        args.ref_steps_per_proc = max(200, min(args.ref_steps_per_proc, budget_calls // max(args.steps, 1)))
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
         return run_reference(args)
     args.steps = 50000 if args.steps is None else args.steps
     args.warmup = 200 if args.warmup is None else max(args.warmup, 3)
