@@ -216,11 +216,30 @@ G2048_DEV void orient(const Sel4 s, uint32_t r0, uint32_t r1, uint32_t r2, uint3
 }
 
 // ---- shift (:243-260) on four lines at once -----------------------------------------
-// if x == 0 (per byte): x <- y, y <- 0
-G2048_DEV void bubble(uint32_t& x, uint32_t& y) {
-  const uint32_t m = nzmask(x);
-  x |= y & ~m;
-  y &= m;
+// Compaction (:250-251): every tile moves toward a by the number of empty cells in front of it
+// (0..3).  Done as a two-stage logarithmic shifter instead of six dependent conditional swaps:
+// stage 1 moves a tile by one place if that number is odd, stage 2 by two places if it is >= 2.
+// za, zb, zc = 0xFF in every byte lane where a, b, c is empty.  A destination is always empty
+// when a tile arrives (its own tile has left, or it was a hole), so OR inserts the tile.
+//   tiles in front of b: za            -> b moves 1 if za
+//   in front of c: za + zb             -> c moves 1 if za ^ zb, then 2 if za & zb
+//   in front of d: za + zb + zc        -> d moves 1 if za ^ zb ^ zc, then 2 if at least two are set
+// (with all three set d has already moved to c in stage 1, and c's rule za & zb carries it on to a;
+//  the stage-2 rule for slot d then moves an empty byte, which is harmless).
+G2048_DEV void compact(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  const uint32_t za = ~nzmask(a), zb = ~nzmask(b), zc = ~nzmask(c);
+  const uint32_t oc = za ^ zb;                     // c moves one place
+  const uint32_t od = oc ^ zc;                     // d moves one place
+  const uint32_t a1 = a | (b & za);
+  const uint32_t b1 = (b & ~za) | (c & oc);
+  const uint32_t c1 = (c & ~oc) | (d & od);
+  const uint32_t d1 = d & ~od;
+  const uint32_t tc = za & zb;                                    // slot c moves on to a
+  const uint32_t td = (za & zb) | (za & zc) | (zb & zc);          // slot d moves on to b
+  a = a1 | (c1 & tc);
+  b = b1 | (d1 & td);
+  c = c1 & ~tc;
+  d = d1 & ~td;
 }
 
 // 2^e (e = byte k of the biased slot word, 0 where the slot is empty) as a float: the byte is
@@ -246,10 +265,7 @@ G2048_DEV float slots_sum(uint32_t slots, uint32_t filled_mask) {
 // Slide (a,b,c,d) toward a with merging; returns the move score (:254) as an exact float
 // (a sum of at most 8 powers of two <= 2^18).
 G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  // compaction: bubble the zeros toward d (3+2+1 conditional moves) (:250-251)
-  bubble(a, b); bubble(b, c); bubble(c, d);
-  bubble(a, b); bubble(b, c);
-  bubble(a, b);
+  compact(a, b, c, d);
   // merges on the compacted line: leftmost pair first, each tile merges once (:252-259)
   //   m1: a==b!=0;  m2: b==c!=0 and not m1;  m3: c==d!=0 and not m2   (bit 7 of each byte)
   const uint32_t m1 = ~addf(a ^ b, L7) & addf(b, L7);

@@ -10,7 +10,18 @@
 
 using namespace g2048;
 
-enum Mode { FULL = 0, MEM_ONLY = 1, NO_PHILOX = 2, NO_SPAWN = 3, NO_MOVE = 4, NO_SCORE = 5, PHILOX_ONLY = 6, NO_LOADS = 7 };
+enum Mode { FULL = 0, MEM_ONLY = 1, NO_PHILOX = 2, NO_SPAWN = 3, NO_MOVE = 4, NO_SCORE = 5, PHILOX_ONLY = 6, NO_LOADS = 7, P2X32 = 8, PSHARE4 = 9 };
+
+// Philox2x32-10 (Random123): what the step would cost with the narrower generator (experiment only)
+__device__ __forceinline__ Words philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+    c0 = hi ^ key ^ c1; c1 = lo; key += 0x9E3779B9u;
+  }
+  return Words{c0, c1, c1 * 0x9E3779B9u, 0};
+}
+
 
 struct P {
   uint4* boards; const uint8_t* actions; float* rewards; uint8_t* dones;
@@ -30,6 +41,8 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
   uint4 bd; uint32_t action;
   if (MODE == NO_LOADS) { bd = make_uint4(i * 0x01010101u & 0x03030303u, 0x01020102u, i & 0x07070707u, 0x00010203u); action = i; }
   else { bd = p.boards[i]; action = p.actions[i]; }
+  Words wq = Words{0, 0, 0, 0};
+  uint32_t it = 0;
   while (true) {
     const uint32_t i_next = i + stride;
     const bool more = i_next < n;
@@ -39,7 +52,14 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
       else { bd_next = p.boards[i_next]; action_next = p.actions[i_next]; }
     }
     Words w;
-    if (MODE == NO_PHILOX || MODE == MEM_ONLY) { w = Words{i * 0x9E3779B9u ^ (uint32_t)p.step_index, i * 0x85EBCA6Bu, i * 0xC2B2AE35u, 0}; }
+    if (MODE == P2X32) { w = philox2x32_10(i, (uint32_t)p.step_index, p.rk.k0[0]); }
+    else if (MODE == PSHARE4) {
+      // one Philox4x32 block per 4 iterations of this thread, words rotated (cost model of block sharing)
+      if ((it & 3u) == 0u) wq = philox4x32_10_rk((uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), i, 0u, p.rk);
+      else { const uint32_t t = wq.w0; wq.w0 = wq.w1; wq.w1 = wq.w2; wq.w2 = wq.w3; wq.w3 = t; }
+      w = wq;
+    }
+    else if (MODE == NO_PHILOX || MODE == MEM_ONLY) { w = Words{i * 0x9E3779B9u ^ (uint32_t)p.step_index, i * 0x85EBCA6Bu, i * 0xC2B2AE35u, 0}; }
     else w = philox4x32_10_rk((uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), i, 0u, p.rk);
     float reward; bool done;
     if (MODE == MEM_ONLY) {
@@ -69,6 +89,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
       p.boards[i] = bd; p.rewards[i] = reward; p.dones[i] = done ? 1 : 0;
     }
     if (!more) break;
+    ++it;
     i = i_next; bd = bd_next; action = action_next;
   }
 }
@@ -131,6 +152,8 @@ int main(int argc, char** argv) {
   printf("== ablations at 1 Mi boards, 8 sets (HBM), 512x2, PDL\n");
   RUN(FULL, 512, 2, 8, true); RUN(MEM_ONLY, 512, 2, 8, true); RUN(NO_PHILOX, 512, 2, 8, true); RUN(NO_SPAWN, 512, 2, 8, true);
   RUN(NO_MOVE, 512, 2, 8, true); RUN(NO_SCORE, 512, 2, 8, true); RUN(PHILOX_ONLY, 512, 2, 8, true); RUN(NO_LOADS, 512, 2, 8, true);
+  RUN(P2X32, 512, 2, 8, true); RUN(PSHARE4, 512, 2, 8, true); RUN(FULL, 512, 2, 8, true);
+  if (argc > 1) return 0;
   printf("== 1 set (L2 resident)\n");
   RUN(FULL, 512, 2, 1, true); RUN(MEM_ONLY, 512, 2, 1, true);
   printf("== no PDL\n");
