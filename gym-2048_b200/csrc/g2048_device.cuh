@@ -248,14 +248,15 @@ template <int K> G2048_DEV float slot_pow2(uint32_t biased) {
   constexpr uint32_t EXPF = 0x7F800000u;
   uint32_t bits;
   if (K == 3) bits = shr<1>(biased) & EXPF;
+  else if (K == 0) bits = shl<23>(biased);      // only bit 8 of `biased` survives below the field: the sign
   else bits = shl<23 - 8 * K>(biased) & EXPF;
-#ifdef G2048_HOST_SIM
   float f;
+#ifdef G2048_HOST_SIM
   __builtin_memcpy(&f, &bits, 4);
-  return f;
 #else
-  return __uint_as_float(bits);
+  f = __uint_as_float(bits);
 #endif
+  return K == 0 ? __builtin_fabsf(f) : f;       // |x| is an operand modifier of FADD: no instruction
 }
 G2048_DEV float slots_sum(uint32_t slots, uint32_t filled_mask) {
   const uint32_t biased = addf(slots, filled_mask & L7);     // e + 127 where filled (<= 145: no carry)
