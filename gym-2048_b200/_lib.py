@@ -17,13 +17,13 @@ HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_PKG, "c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_AUTO_RESET = 1
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
     "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
-    "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox",
+    "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
     "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return", "g2048_gae",
@@ -123,6 +123,8 @@ def lib():
     L.g2048_values_from_exp.argtypes = [vp, vp, u64, vp]
     L.g2048_exp_from_values.argtypes = [vp, vp, u64, vp, vp]
     L.g2048_philox.argtypes = [vp, u32, u32, vp, u64, vp]
+    L.g2048_philox2x32.argtypes = [vp, u32, vp, u64, vp]
+    L.g2048_draw_words.argtypes = [vp, u64, u64, u64, u64, u32, vp]
     L.g2048_env_create.argtypes = [C.POINTER(vp), C.POINTER(EnvConfig)]
     L.g2048_env_destroy.argtypes = [vp]
     L.g2048_env_reset_host.argtypes = [vp, vp]

@@ -92,9 +92,9 @@ struct StepParams {
   uint64_t* step_counter;       // [0] step index, [1] CTA arrival ticket (0 between launches)
   uint32_t n;                   // < 2^32 - 256 (checked by the host)
   uint32_t env_lo;              // low half of the env id of board 0; the launch never crosses 2^32
-  uint32_t env_hi;              // high half (counter word 3, tag bit clear), the same for every board
-  RoundKeys rk;                 // Philox round keys of `seed`
-  PhiloxHead head;              // launch-uniform part of Philox rounds 0-1 for (seed, step_index, env_hi)
+  uint32_t env_hi;              // high half, the same for every board
+  uint64_t seed;                // only read when step_counter is set (the key is then derived on the device)
+  StreamKeys keys;              // Philox2x32 round keys of stream_key(seed, step_index, env_hi, TAG_STEP)
   float illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t flags;
@@ -125,16 +125,20 @@ __device__ __forceinline__ uint4 load_board(const uint4* ptr) {
 }
 
 // One board, already rotated into its move frame (a,b,c,d), through Game2048Env.step and out to memory.
-template <bool EXTRAS>
+// COUNTER: the step index is read from device memory (CUDA-graph replay), so the generator's key
+// and counter word 1 are registers (dev_key, dev_idx_lo) instead of kernel-parameter constants.
+template <bool EXTRAS, bool COUNTER>
 __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
                                                uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
-                                               const PhiloxHead& head, bool auto_reset) {
+                                               uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
   Words w;
   if (EXTRAS && p.forced_draws) {
     const uint4 f = p.forced_draws[i];
     w = Words{f.x, f.y, f.z, f.w};
+  } else if (COUNTER) {
+    w = words_from_pair(philox2x32_10(p.env_lo + i, dev_idx_lo, dev_key));
   } else {
-    w = philox4x32_10_head(p.env_lo + i, head, p.rk);
+    w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.keys));
   }
   uint4 bd;
   const StepOut o = step_oriented(lut, a, b, c, d, so, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr,
@@ -167,7 +171,7 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
 #define G2048_PTR_INC 0      //    kernel parameters (LDC) and re-deriving the addresses every iteration.  Measured:
 #endif                       //    smem selectors -1.2 %, pointer walk -0.7 %, both together -0.6 % -> selectors only
 
-template <bool EXTRAS>
+template <bool EXTRAS, bool COUNTER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
   __shared__ Board4 s_lut[32];
   __shared__ Sel4 s_sel[8];     // [action] = kOrientIn, [4 + action] = kOrientOut
@@ -187,11 +191,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
-  PhiloxHead head = p.head;
   uint64_t counter_value = 0;
-  if (p.step_counter) {                     // device-side step index (CUDA-graph replay), launch-uniform branch
+  uint32_t dev_key = 0u, dev_idx_lo = 0u;
+  if (COUNTER) {                            // device-side step index (CUDA-graph replay)
     counter_value = p.step_counter[0];
-    head = make_philox_head(counter_value, p.env_hi, p.rk);
+    dev_key = stream_key(p.seed, counter_value, (uint64_t)p.env_hi << 32, TAG_STEP);
+    dev_idx_lo = (uint32_t)counter_value;
     __syncthreads();                        // every thread of the CTA has read the index before thread 0 can arrive
   }
   if (i >= n) return;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
     }
 #endif
-    step_and_store<EXTRAS>(p, lut, i, a, b, c, d, so, head, auto_reset);
+    step_and_store<EXTRAS, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
     if (!more) break;
 #if !G2048_PREFETCH
     bd = load_board(p.boards + i_next); action = p.actions[i_next];
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   }
   // The last CTA to arrive advances the device-side step index: by then every CTA has read it.
   // (Thread 0 of a CTA always owns a board, so it never took the early exit above.)
-  if (p.step_counter && (p.flags & kFlagBumpCounter) && threadIdx.x == 0) {
+  if (COUNTER && (p.flags & kFlagBumpCounter) && threadIdx.x == 0) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(p.step_counter + 1);
     if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
       *ticket = 0u;
@@ -250,9 +255,10 @@ g2048_reset_kernel(uint4* boards, const uint8_t* reset_mask, uint64_t n, uint64_
   __shared__ Board4 s_lut[32];
   const Board4* lut = make_reset_lut(s_lut);
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  DrawStream draws(seed, reset_index, TAG_RESET);
   for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     if (reset_mask && !reset_mask[i]) continue;
-    const Words w = draw_words(seed, env_id_base + i, reset_index, 1u);
+    const Words w = draws.words(env_id_base + i);
     uint4 bd;
     fresh_board(lut, w.w1, w.w2, bd.x, bd.y, bd.z, bd.w);
     boards[i] = bd;
@@ -263,9 +269,10 @@ g2048_reset_kernel(uint4* boards, const uint8_t* reset_mask, uint64_t n, uint64_
 __global__ void __launch_bounds__(kThreads)
 g2048_add_tile_kernel(uint4* boards, uint64_t n, uint64_t env_id_base, uint64_t seed, uint64_t step_index) {
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  DrawStream draws(seed, step_index, TAG_STEP);
   for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     uint4 bd = boards[i];
-    const Words w = draw_words(seed, env_id_base + i, step_index, 0u);
+    const Words w = draws.words(env_id_base + i);
     spawn(bd.x, bd.y, bd.z, bd.w, w.w0);
     boards[i] = bd;
   }
@@ -386,6 +393,26 @@ g2048_philox_kernel(const uint4* ctr, uint32_t k0, uint32_t k1, uint4* out, uint
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+g2048_philox2x32_kernel(const uint2* ctr, uint32_t key, uint2* out, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint2 c = ctr[i];
+    const Pair x = philox2x32_10(c.x, c.y, key);
+    out[i] = make_uint2(x.x0, x.x1);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+g2048_draw_words_kernel(uint4* out, uint64_t n, uint64_t env_id_base, uint64_t seed, uint64_t idx, uint32_t tag) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  DrawStream draws(seed, idx, tag);
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const Words w = draws.words(env_id_base + i);
+    out[i] = make_uint4(w.w0, w.w1, w.w2, w.w3);
+  }
+}
+
 int launch_check(const char* name) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, name);
@@ -454,9 +481,9 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   p.step_counter = a->step_counter;
   p.n = (uint32_t)a->n;
   p.env_lo = (uint32_t)a->env_id_base;
-  p.env_hi = (uint32_t)(a->env_id_base >> 32) & 0x7FFFFFFFu;
-  make_round_keys(a->seed, p.rk);
-  p.head = make_philox_head(a->step_index, p.env_hi, p.rk);
+  p.env_hi = (uint32_t)(a->env_id_base >> 32);
+  p.seed = a->seed;
+  make_stream_keys(stream_key(a->seed, a->step_index, a->env_id_base, TAG_STEP), (uint32_t)a->step_index, p.keys);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = (a->flags & ~kFlagBumpCounter) | (bump_counter ? kFlagBumpCounter : 0u);
@@ -478,8 +505,12 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 #endif
-  const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<true>, p)
-                                : cudaLaunchKernelEx(&cfg, g2048_step_kernel<false>, p);
+  const bool counter = a->step_counter != nullptr;
+  const cudaError_t le =
+      extras ? (counter ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<true, true>, p)
+                        : cudaLaunchKernelEx(&cfg, g2048_step_kernel<true, false>, p))
+             : (counter ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<false, true>, p)
+                        : cudaLaunchKernelEx(&cfg, g2048_step_kernel<false, false>, p));
   if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_kernel)");
   return G2048_OK;
 }
@@ -595,6 +626,26 @@ int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* ou
   g2048_philox_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(ctr), key0, key1, reinterpret_cast<uint4*>(out), n);
   return launch_check("g2048_philox_kernel");
+}
+
+int g2048_philox2x32(const uint32_t* ctr, uint32_t key, uint32_t* out, uint64_t n, void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!ctr || !out) return fail(G2048_ERR_INVALID, "g2048_philox2x32: NULL pointer");
+  if (((uintptr_t)ctr | (uintptr_t)out) & 7u) return fail(G2048_ERR_ALIGN, "g2048_philox2x32: 8-byte alignment required");
+  g2048_philox2x32_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(ctr), key, reinterpret_cast<uint2*>(out), n);
+  return launch_check("g2048_philox2x32_kernel");
+}
+
+int g2048_draw_words(uint32_t* words, uint64_t n, uint64_t env_id_base, uint64_t seed, uint64_t index, uint32_t tag,
+                     void* stream) {
+  if (n == 0) return G2048_OK;
+  if (!words) return fail(G2048_ERR_INVALID, "g2048_draw_words: words is NULL");
+  if (!aligned16(words)) return fail(G2048_ERR_ALIGN, "g2048_draw_words: words must be 16-byte aligned");
+  if (tag > 2u) return fail(G2048_ERR_INVALID, "g2048_draw_words: tag %u is not a stream tag (0 step, 1 reset, 2 policy)", tag);
+  g2048_draw_words_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(words), n, env_id_base, seed, index, tag);
+  return launch_check("g2048_draw_words_kernel");
 }
 
 // ---- stateful host-buffer API ---------------------------------------------------------

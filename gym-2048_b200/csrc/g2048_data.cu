@@ -12,14 +12,16 @@ namespace g2048 {
 
 // ---- random policies ------------------------------------------------------------------
 // train.py:119 `random.randint(0, 3)` / the random-legal policy of BASELINE config 4, drawn
-// from word 3 of the step-tag Philox block (word 0 of the same block is the step's spawn).
+// from word 0 of the policy-tag draw stream at the step's index (its own stream: independent of
+// the spawn the step makes with the step-tag words).
 __global__ void __launch_bounds__(kThreads)
 g2048_sample_actions_kernel(const uint8_t* legal_mask, uint8_t* actions, uint64_t n, uint64_t env_id_base,
                             uint64_t seed, uint64_t step_index) {
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  DrawStream draws(seed, step_index, TAG_POLICY);
   for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const Words w = draw_words(seed, env_id_base + i, step_index, 0u);
-    actions[i] = (uint8_t)pick_action(legal_mask ? legal_mask[i] : 15u, w.w3);
+    const Words w = draws.words(env_id_base + i);
+    actions[i] = (uint8_t)pick_action(legal_mask ? legal_mask[i] : 15u, w.w0);
   }
 }
 

@@ -90,95 +90,108 @@ G2048_DEV uint32_t spread(uint32_t x) { return prmt(x, 0u, 0xBA98u); }
 // 0xFF where the byte of x is non-zero (bytes of x <= 0x80).
 G2048_DEV uint32_t nzmask(uint32_t x) { return spread(addf(x, L7)); }
 
-// ---- Philox4x32-10 (Salmon et al. SC'11) ------------------------------------------
+// ---- draw stream: Philox (Salmon et al. SC'11, Random123 constants) ---------------------------
+// Two generators of the family.  Philox4x32-10 runs ONCE PER LAUNCH (on the host, or in the
+// kernel prologue when the step index lives on the device) and compresses everything that is
+// the same for every board of a launch — seed, high halves of the step index and of the env id,
+// stream tag — into one 32-bit key.  Philox2x32-10, keyed with it and counting (env_lo, idx_lo),
+// runs once per board: 10 wide multiplies instead of 20, and 64 output bits are all a step needs
+// (32 for the spawn, 32 for the two spawns of a reset).
 struct Words { uint32_t w0, w1, w2, w3; };
 
-G2048_DEV Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+G2048_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+G2048_HD Words philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
     c1 = lo1;
     c2 = hi0 ^ c3 ^ k1;
     c3 = lo0;
-    k0 += 0x9E3779B9u;   // key schedule is warp-uniform: folded into constants
+    k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
   return Words{c0, c1, c2, c3};
 }
 
-// Same with the 10 round keys precomputed (host side, passed in kernel-parameter constant
-// memory): the key schedule then costs no instruction at all in the hot loop.
-struct RoundKeys { uint32_t k0[10], k1[10]; };
-G2048_DEV Words philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RoundKeys& rk) {
+constexpr uint32_t PHILOX2_M = 0xD256D193u, PHILOX_W = 0x9E3779B9u;
+struct Pair { uint32_t x0, x1; };
+
+G2048_HD Pair philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ rk.k0[r];
-    c1 = lo1;
-    c2 = hi0 ^ c3 ^ rk.k1[r];
-    c3 = lo0;
+    const uint32_t hi = mulhi32(PHILOX2_M, c0), lo = PHILOX2_M * c0;
+    c0 = hi ^ key ^ c1;
+    c1 = lo;
+    key += PHILOX_W;
   }
-  return Words{c0, c1, c2, c3};
-}
-G2048_HD void make_round_keys(uint64_t seed, RoundKeys& rk) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  for (int r = 0; r < 10; ++r) {
-    rk.k0[r] = k0; rk.k1[r] = k1;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
+  return Pair{c0, c1};
 }
 
-// Within one launch only counter word 2 (the low half of the env id) differs between boards:
-// c0,c1 = step index and c3 = high half of the env id (| tag) are the same for every board, as
-// long as the launch does not straddle a 2^32 boundary of env ids (the host splits it there).
-// Round 0 then has one varying product (M1 * env_lo) and round 1 one (M0 * c0'); everything else
-// of those two rounds folds into four words computed once per launch:
-//   round 0: c0' = hi(M1*env_lo) ^ A        c1' = lo(M1*env_lo)   c2' = B (uniform)   c3' = C (uniform)
-//   round 1: c0" = c1' ^ E                  c1" = lo(M1*B) (uniform, folded into G)
-//            c2" = hi(M0*c0') ^ F           c3" = lo(M0*c0')
-//   round 2: c0 = hi(M1*c2") ^ G, the rest as usual.
-// Saves 2 of the 20 wide multiplies, a 64-bit add and two logic ops per board.
-struct PhiloxHead { uint32_t A, E, F, G; };
-G2048_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-G2048_HD PhiloxHead make_philox_head(uint64_t idx, uint32_t c3, const RoundKeys& rk) {
-  const uint32_t s_lo = (uint32_t)idx, s_hi = (uint32_t)(idx >> 32);
-  const uint32_t B = mulhi32(0xD2511F53u, s_lo) ^ c3 ^ rk.k1[0];
-  const uint32_t Cw = 0xD2511F53u * s_lo;
-  PhiloxHead h;
-  h.A = s_hi ^ rk.k0[0];
-  h.E = mulhi32(0xCD9E8D57u, B) ^ rk.k0[1];
-  h.F = Cw ^ rk.k1[1];
-  h.G = (0xCD9E8D57u * B) ^ rk.k0[2];
-  return h;
+// Stream tags: which consumer the words are for.
+constexpr uint32_t TAG_STEP = 0u, TAG_RESET = 1u, TAG_POLICY = 2u;
+
+// The launch-uniform key (include/g2048.h "Draw stream").
+G2048_HD uint32_t stream_key(uint64_t seed, uint64_t idx, uint64_t env_id, uint32_t tag) {
+  return philox4x32_10((uint32_t)(idx >> 32), (uint32_t)(env_id >> 32), tag, 0u, (uint32_t)seed,
+                       (uint32_t)(seed >> 32)).w0;
 }
-G2048_DEV Words philox4x32_10_head(uint32_t env_lo, const PhiloxHead& h, const RoundKeys& rk) {
-  const uint32_t c0a = __umulhi(0xCD9E8D57u, env_lo) ^ h.A, c1a = 0xCD9E8D57u * env_lo;     // round 0
-  const uint32_t c0b = c1a ^ h.E;                                                             // round 1
-  const uint32_t c2b = __umulhi(0xD2511F53u, c0a) ^ h.F, c3b = 0xD2511F53u * c0a;
-  uint32_t c0 = __umulhi(0xCD9E8D57u, c2b) ^ h.G, c1 = 0xCD9E8D57u * c2b;                    // round 2
-  uint32_t c2 = __umulhi(0xD2511F53u, c0b) ^ c3b ^ rk.k1[2], c3 = 0xD2511F53u * c0b;
+
+// The per-board generator with the ten round keys precomputed (host side, passed in
+// kernel-parameter constant memory, so the key schedule costs no instruction in the hot loop)
+// and counter word 1 — the low half of the step index, the same for every board — folded into
+// round 0's key: round 0 is then one wide multiply and one two-input XOR.
+struct StreamKeys { uint32_t k[10]; };        // k[0] = key ^ idx_lo, k[r] = key + r * W
+G2048_HD void make_stream_keys(uint32_t key, uint32_t idx_lo, StreamKeys& ks) {
+  ks.k[0] = key ^ idx_lo;
+  for (int r = 1; r < 10; ++r) ks.k[r] = key + (uint32_t)r * PHILOX_W;
+}
+G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, const StreamKeys& ks) {
+  uint32_t c0 = mulhi32(PHILOX2_M, env_lo) ^ ks.k[0], c1 = PHILOX2_M * env_lo;
 #pragma unroll
-  for (int r = 3; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ rk.k0[r];
-    c1 = lo1;
-    c2 = hi0 ^ c3 ^ rk.k1[r];
-    c3 = lo0;
+  for (int r = 1; r < 10; ++r) {
+    const uint32_t hi = mulhi32(PHILOX2_M, c0), lo = PHILOX2_M * c0;
+    c0 = hi ^ ks.k[r] ^ c1;
+    c1 = lo;
   }
-  return Words{c0, c1, c2, c3};
+  return Pair{c0, c1};
 }
+
+// Draw words from the generator output: w0 = x0 spawns after a legal move; a reset spawns with
+// w1 = x1 and then w2 = x1 << 16 (the first spawn reads x1 from the top — 4 bits of cell, then the
+// 2-or-4 fraction —, the second starts at bit 15; the two only share bits below 2^-12 of the first
+// fraction's resolution).  w3 is unused (0).
+G2048_HD Words words_from_pair(const Pair x) { return Words{x.x0, x.x1, x.x1 << 16, 0u}; }
 
 // Draw words for (seed, global env id, index, tag) — include/g2048.h "Draw stream".
-G2048_DEV Words draw_words(uint64_t seed, uint64_t env_id, uint64_t idx, uint32_t tag) {
-  return philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)env_id,
-                       ((uint32_t)(env_id >> 32) & 0x7FFFFFFFu) | (tag << 31),
-                       (uint32_t)seed, (uint32_t)(seed >> 32));
+G2048_HD Words draw_words(uint64_t seed, uint64_t env_id, uint64_t idx, uint32_t tag) {
+  return words_from_pair(philox2x32_10((uint32_t)env_id, (uint32_t)idx, stream_key(seed, idx, env_id, tag)));
 }
+
+// The same for a loop over many boards of one (seed, idx, tag): the launch-uniform key is
+// recomputed only when the high half of the env id changes (at most once per 2^32 boards).
+struct DrawStream {
+  uint64_t seed, idx;
+  uint32_t tag, env_hi, key;
+  bool have_key;
+  G2048_HD DrawStream(uint64_t seed_, uint64_t idx_, uint32_t tag_)
+      : seed(seed_), idx(idx_), tag(tag_), env_hi(0u), key(0u), have_key(false) {}
+  G2048_HD Words words(uint64_t env_id) {
+    const uint32_t hi = (uint32_t)(env_id >> 32);
+    if (!have_key || hi != env_hi) {
+      env_hi = hi;
+      key = stream_key(seed, idx, env_id, tag);
+      have_key = true;
+    }
+    return words_from_pair(philox2x32_10((uint32_t)env_id, (uint32_t)idx, key));
+  }
+};
 
 // ---- orientation --------------------------------------------------------------------
 // move() (:210-237) shifts every line toward one side.  We rotate the board into a

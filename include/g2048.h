@@ -21,20 +21,26 @@
  *     arrays must be 16-byte aligned.  g2048_values_from_exp/exp_from_values
  *     convert to/from the reference's 4x4 int64 tile VALUES (Matrix).
  *   - actions: 0=Up 1=Right 2=Down 3=Left (game2048_env.py:210-212).
- *   - determinism: spawn draws are Philox4x32-10 words addressed by
+ *   - determinism: spawn draws are counter-based Philox words addressed by
  *     (seed, global env id, step index); results do not depend on how the batch
  *     is sharded over GPUs (env_id_base = global id of element 0).
  *
- * Draw stream (frozen, version 1) — see DESIGN.md §3:
- *   w[0..3] = philox4x32_10(ctr = {idx_lo, idx_hi, env_lo, env_hi | tag<<31},
- *                           key = {seed_lo, seed_hi})
- *   tag 0: idx = step_index (g2048_step);   tag 1: idx = reset_index (g2048_reset)
+ * Draw stream (frozen, version 2; ABI >= 3) — see DESIGN.md §3.  Philox as
+ * published (Salmon et al., SC'11; Random123 constants and known-answer vectors):
+ *   key      = philox4x32_10(ctr = {idx_hi, env_hi, tag, 0},
+ *                            key = {seed_lo, seed_hi}).word0   [the same for a whole launch]
+ *   (x0, x1) = philox2x32_10(ctr = {env_lo, idx_lo}, key)      [once per board]
+ *   w[0] = x0,  w[1] = x1,  w[2] = x1 << 16,  w[3] = 0
+ *   tag 0: idx = step_index (g2048_step, g2048_add_tile)
+ *   tag 1: idx = reset_index (g2048_reset)
+ *   tag 2: idx = step_index (g2048_sample_actions: policy word w[0])
  *   spawn(board, w): n = #empty cells; p = (uint64)w * n; k = p >> 32;
  *                    f = (uint32)p;  tile = (f < 3865470567u) ? 2 : 4   [P(2)=0.9]
  *                    the k-th empty cell in row-major order receives the tile.
  *   step spawn uses w[0]; a reset (auto-reset in g2048_step, or g2048_reset)
- *   zeroes the board and spawns with w[1] then w[2].  w[3] of the step-tag block
- *   is the policy word of g2048_sample_actions (random / random-legal actions).
+ *   zeroes the board and spawns with w[1] then w[2].
+ *   (Version 1, ABI <= 2, drew all four words from one philox4x32_10 block per
+ *   board; version 2 halves the generator's work per board.)
  */
 #ifndef G2048_H
 #define G2048_H
@@ -46,7 +52,12 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 2 /* 2: G2048StepArgs.boards_out, data-side entry points */
+#define G2048_ABI_VERSION 3 /* 2: G2048StepArgs.boards_out, data-side entry points */
+                            /* 3: draw stream version 2, g2048_philox2x32, g2048_draw_words */
+
+#define G2048_TAG_STEP   0u
+#define G2048_TAG_RESET  1u
+#define G2048_TAG_POLICY 2u
 
 #define G2048_OK            0
 #define G2048_ERR_INVALID  (-1) /* bad argument (NULL required pointer, bad dtype, ...) */
@@ -86,8 +97,8 @@ typedef struct G2048StepArgs {
   uint32_t*       ep_len;          /* [n]    in/out, nullable: running episode length      */
   uint32_t*       final_score;     /* [n]    out, nullable: episode score, where done      */
   uint32_t*       final_len;       /* [n]    out, nullable: episode length, where done     */
-  const uint32_t* forced_draws;    /* [n*4]  nullable: words used INSTEAD of the Philox    */
-                                   /*        output w[0..3] (fixture / CSV parity)         */
+  const uint32_t* forced_draws;    /* [n*4]  nullable: words used INSTEAD of the draw      */
+                                   /*        words w[0..3] (fixture / CSV parity)          */
   uint64_t*       step_counter;    /* nullable device uint64[2]: when set the step index is */
                                    /*        read from step_counter[0] instead of step_index */
                                    /*        and the launch itself advances it when it ends  */
@@ -95,8 +106,8 @@ typedef struct G2048StepArgs {
                                    /*        of the library and must be 0 before the 1st use */
   uint64_t        n;               /* boards in this call                                  */
   uint64_t        env_id_base;     /* global env id of element 0                           */
-  uint64_t        seed;            /* Philox key                                           */
-  uint64_t        step_index;      /* Philox counter low 64 bits; caller increments        */
+  uint64_t        seed;            /* draw-stream seed                                     */
+  uint64_t        step_index;      /* draw-stream index; caller increments                 */
   float           illegal_move_reward; /* set_illegal_move_reward (:61-67), default 0      */
   uint32_t        max_tile_exp;    /* set_max_tile (:69-73) as exponent; 0 = None          */
   uint32_t        flags;           /* G2048_FLAG_*                                         */
@@ -165,6 +176,13 @@ int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cel
 /* Debug: out[4*i..4*i+3] = philox4x32_10(ctr[4*i..], key) — known-answer tests. */
 int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* out,
                  uint64_t n, void* stream);
+/* Debug: out[2*i..2*i+1] = philox2x32_10(ctr[2*i..], key) — known-answer tests (8-byte aligned). */
+int g2048_philox2x32(const uint32_t* ctr, uint32_t key, uint32_t* out, uint64_t n,
+                     void* stream);
+/* The draw words w[0..3] of env ids env_id_base .. env_id_base+n-1 at `index` under `tag`
+ * (G2048_TAG_*), as the kernels compute them: words[4*i..4*i+3], 16-byte aligned. */
+int g2048_draw_words(uint32_t* words, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                     uint64_t index, uint32_t tag, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Either side of the step: the random policies that drive it and the        */
@@ -176,8 +194,9 @@ int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* ou
  * {0,1,2,3} (train.py:119 `random.randint(0, 3)`, the benchmark's random
  * actions).  legal_mask given: uniform among the set bits of legal_mask[i] (all
  * four when the mask is 0) — the random-legal policy of BASELINE config 4.
- * action = the k-th set bit, k = hi32(w[3] * popcount), w = the step-tag draw
- * words of (seed, env id, step_index) (the same block g2048_step uses w[0] of).
+ * action = the k-th set bit, k = hi32(w[0] * popcount), w = the policy-tag draw
+ * words of (seed, env id, step_index): a stream of its own, independent of the
+ * spawn g2048_step makes at the same index.
  */
 int g2048_sample_actions(const uint8_t* legal_mask, uint8_t* actions, uint64_t n,
                          uint64_t env_id_base, uint64_t seed, uint64_t step_index,

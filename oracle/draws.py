@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-* `philox4x32_10` / `draw_words` restate the draw stream frozen in include/g2048.h
-  (Philox4x32-10, Salmon et al. SC'11, Random123 constants) with vectorised uint64
+* `philox4x32_10` / `philox2x32_10` / `draw_words` restate the draw stream frozen in
+  include/g2048.h (version 2: a launch-uniform key from Philox4x32-10, one Philox2x32-10
+  block per board; Salmon et al. SC'11, Random123 constants) with vectorised uint64
   arithmetic; pinned by the Random123 known-answer vectors in tests/test_draws.py.
 * `InjectedDraws` is assigned to `env.np_random` of the UNMODIFIED reference env.
   The reference's add_tile (game2048_env.py:166-176) only calls `.random()` (:168)
@@ -37,15 +38,45 @@ def philox4x32_10(ctr, key):
     return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
 
 
-def draw_words(seed, env_ids, idx, tag):
-    """Words w[0..3] for global env ids `env_ids` at step/reset index `idx` (tag 0/1)."""
+M2 = 0xD256D193
+TAG_STEP, TAG_RESET, TAG_POLICY = 0, 1, 2
+
+
+def philox2x32_10(ctr, key):
+    """ctr: (..., 2) uint32, key: (...) or scalar uint32 -> (..., 2) uint32."""
+    ctr = np.asarray(ctr, dtype=np.uint64)
+    c0, c1 = ctr[..., 0].copy(), ctr[..., 1].copy()
+    key = np.broadcast_to(np.asarray(key, dtype=np.uint64) & np.uint64(MASK32), c0.shape).copy()
+    for _ in range(10):
+        p = np.uint64(M2) * c0
+        c0 = (p >> np.uint64(32)) ^ key ^ c1
+        c1 = p & np.uint64(MASK32)
+        key = (key + np.uint64(W0)) & np.uint64(MASK32)
+    return np.stack([c0, c1], axis=-1).astype(np.uint32)
+
+
+def stream_keys(seed, env_ids, idx, tag):
+    """The launch-uniform 32-bit key of every env id (it only depends on the id's high half)."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
-    ctr = np.empty(env_ids.shape + (4,), dtype=np.uint64)
-    ctr[..., 0] = int(idx) & MASK32
-    ctr[..., 1] = (int(idx) >> 32) & MASK32
-    ctr[..., 2] = env_ids & np.uint64(MASK32)
-    ctr[..., 3] = ((env_ids >> np.uint64(32)) & np.uint64(0x7FFFFFFF)) | np.uint64((int(tag) & 1) << 31)
-    return philox4x32_10(ctr, (int(seed) & MASK32, (int(seed) >> 32) & MASK32))
+    kctr = np.zeros(env_ids.shape + (4,), dtype=np.uint64)
+    kctr[..., 0] = (int(idx) >> 32) & MASK32
+    kctr[..., 1] = env_ids >> np.uint64(32)
+    kctr[..., 2] = int(tag)
+    return philox4x32_10(kctr, (int(seed) & MASK32, (int(seed) >> 32) & MASK32))[..., 0]
+
+
+def draw_words(seed, env_ids, idx, tag):
+    """Words w[0..3] for global env ids `env_ids` at step/reset index `idx` under stream `tag`."""
+    env_ids = np.asarray(env_ids, dtype=np.uint64)
+    ctr = np.empty(env_ids.shape + (2,), dtype=np.uint64)
+    ctr[..., 0] = env_ids & np.uint64(MASK32)
+    ctr[..., 1] = int(idx) & MASK32
+    x = philox2x32_10(ctr, stream_keys(seed, env_ids, idx, tag)).astype(np.uint64)
+    w = np.zeros(env_ids.shape + (4,), dtype=np.uint64)
+    w[..., 0] = x[..., 0]
+    w[..., 1] = x[..., 1]
+    w[..., 2] = (x[..., 1] << np.uint64(16)) & np.uint64(MASK32)
+    return w.astype(np.uint32)
 
 
 def spawn_from_word(n_empty, w):

@@ -42,12 +42,30 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* ---- Philox2x32-10 (same paper, same constants table) --------------------- */
+static void philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p = (uint64_t)0xD256D193u * c0;
+    uint32_t n0 = (uint32_t)(p >> 32) ^ key ^ c1;
+    c1 = (uint32_t)p;
+    c0 = n0;
+    key += 0x9E3779B9u;
+  }
+  out[0] = c0; out[1] = c1;
+}
+
+/* Draw stream version 2 (include/g2048.h): a launch-uniform 32-bit key from
+ * Philox4x32-10, then one Philox2x32-10 block per (env, index). */
 static void draw_words(uint64_t seed, uint64_t env_id, uint64_t idx, uint32_t tag,
                        uint32_t w[4]) {
-  uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)env_id,
-                     ((uint32_t)(env_id >> 32) & 0x7FFFFFFFu) | (tag << 31)};
-  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-  philox4x32_10(ctr, key, w);
+  uint32_t kctr[4] = {(uint32_t)(idx >> 32), (uint32_t)(env_id >> 32), tag, 0u};
+  uint32_t kkey[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t kout[4], x[2];
+  philox4x32_10(kctr, kkey, kout);
+  uint32_t ctr[2] = {(uint32_t)env_id, (uint32_t)idx};
+  philox2x32_10(ctr, kout[0], x);
+  w[0] = x[0]; w[1] = x[1]; w[2] = x[1] << 16; w[3] = 0u;
 }
 
 /* ---- shift (:243-260): single pass over one line toward index 0 ----------- */
@@ -306,6 +324,17 @@ int g2048_oracle_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint3
   return G2048_OK;
 }
 
+int g2048_oracle_philox2x32(const uint32_t* ctr, uint32_t key, uint32_t* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) philox2x32_10(ctr + 2 * i, key, out + 2 * i);
+  return G2048_OK;
+}
+
+int g2048_oracle_draw_words(uint32_t* words, uint64_t n, uint64_t env_id_base, uint64_t seed,
+                            uint64_t index, uint32_t tag) {
+  for (uint64_t i = 0; i < n; ++i) draw_words(seed, env_id_base + i, index, tag, words + 4 * i);
+  return G2048_OK;
+}
+
 /* shift() on one line of exponents, for the exhaustive golden table. */
 uint32_t g2048_oracle_shift(const uint8_t row[4], uint8_t out[4]) {
   return shift_line(row, out);
@@ -313,17 +342,18 @@ uint32_t g2048_oracle_shift(const uint8_t row[4], uint8_t out[4]) {
 
 
 /* ---- the random policies that drive the step (train.py:119 random.randint(0, 3); ------------
- *      BASELINE config 4's random-legal policy): k-th allowed action, k from draw word 3 ---- */
+ *      BASELINE config 4's random-legal policy): k-th allowed action, k from word 0 of the
+ *      policy-tag stream ---- */
 int g2048_oracle_sample_actions(const uint8_t* legal_mask, uint8_t* actions, uint64_t n,
                                 uint64_t env_id_base, uint64_t seed, uint64_t step_index) {
   if (!actions) return G2048_ERR_INVALID;
   for (uint64_t i = 0; i < n; ++i) {
     uint32_t w[4];
-    draw_words(seed, env_id_base + i, step_index, 0, w);
+    draw_words(seed, env_id_base + i, step_index, G2048_TAG_POLICY, w);
     int allowed[4], cnt = 0;
     for (int d = 0; d < 4; ++d)
       if (!legal_mask || (legal_mask[i] & 15) == 0 || ((legal_mask[i] >> d) & 1)) allowed[cnt++] = d;
-    uint32_t k = (uint32_t)(((uint64_t)w[3] * (uint64_t)cnt) >> 32);
+    uint32_t k = (uint32_t)(((uint64_t)w[0] * (uint64_t)cnt) >> 32);
     actions[i] = (uint8_t)allowed[k];
   }
   return G2048_OK;

@@ -164,6 +164,22 @@ def philox(ctr, key0, key1):
     return out
 
 
+def philox2x32(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 2)
+    out = np.empty_like(c)
+    rc = lib().g2048_oracle_philox2x32(_p(c), C.c_uint32(key), _p(out), C.c_uint64(len(c)))
+    assert rc == 0
+    return out
+
+
+def draw_words(n, env_id_base, seed, index, tag):
+    out = np.empty((n, 4), np.uint32)
+    rc = lib().g2048_oracle_draw_words(_p(out), C.c_uint64(n), C.c_uint64(env_id_base), C.c_uint64(seed),
+                                       C.c_uint64(index), C.c_uint32(tag))
+    assert rc == 0
+    return out
+
+
 def shift(row_exps):
     r = (C.c_uint8 * 4)(*[int(x) for x in row_exps])
     o = (C.c_uint8 * 4)()

@@ -101,6 +101,20 @@ class SimOps:
         sim_lib().sim_philox(_p(c), C.c_uint32(k0), C.c_uint32(k1), _p(out), C.c_uint64(len(c)))
         return out
 
+    @staticmethod
+    def philox2x32(ctr, key):
+        c = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 2)
+        out = np.empty_like(c)
+        sim_lib().sim_philox2x32(_p(c), C.c_uint32(key), _p(out), C.c_uint64(len(c)))
+        return out
+
+    @staticmethod
+    def draw_words(n, env_id_base, seed, index, tag, form=1):
+        out = np.empty((n, 4), np.uint32)
+        sim_lib().sim_draw_words(_p(out), C.c_uint64(n), C.c_uint64(env_id_base), C.c_uint64(seed), C.c_uint64(index),
+                                 C.c_uint32(tag), C.c_int(form))
+        return out
+
 
 class OracleOps:
     name = "oracle"
@@ -109,6 +123,8 @@ class OracleOps:
     add_tile = staticmethod(oracle.add_tile)
     status = staticmethod(oracle.status)
     philox = staticmethod(oracle.philox)
+    philox2x32 = staticmethod(oracle.philox2x32)
+    draw_words = staticmethod(oracle.draw_words)
 
 
 # ---------------------------------------------------------------------------------------
@@ -222,5 +238,28 @@ class GpuOps:
         out = torch.empty_like(c)
         check(g._lib.lib().g2048_philox(C.c_void_p(c.data_ptr()), k0, k1, C.c_void_p(out.data_ptr()), c.shape[0],
                                         None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    @staticmethod
+    def philox2x32(ctr, key):
+        import ctypes as C
+        import torch
+        import gym_2048_b200 as g
+        from gym_2048_b200._lib import check
+        c = torch.from_numpy(np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 2)).cuda()
+        out = torch.empty_like(c)
+        check(g._lib.lib().g2048_philox2x32(C.c_void_p(c.data_ptr()), key, C.c_void_p(out.data_ptr()), c.shape[0], None))
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+
+    @staticmethod
+    def draw_words(n, env_id_base, seed, index, tag):
+        import ctypes as C
+        import torch
+        import gym_2048_b200 as g
+        from gym_2048_b200._lib import check
+        out = torch.empty((n, 4), dtype=torch.uint32, device="cuda")
+        check(g._lib.lib().g2048_draw_words(C.c_void_p(out.data_ptr()), n, env_id_base, seed, index, tag, None))
         torch.cuda.synchronize()
         return out.cpu().numpy()

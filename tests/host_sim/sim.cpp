@@ -29,11 +29,11 @@ extern "C" int sim_step(const G2048StepArgs* p) {
       const uint32_t* f = p->forced_draws + 4 * i;
       w = Words{f[0], f[1], f[2], f[3]};
     } else {
-      RoundKeys rk;
-      make_round_keys(p->seed, rk);
+      // the kernel's hot-loop form: host-made round keys with idx_lo folded into round 0
       const uint64_t env = p->env_id_base + i, idx = p->step_counter ? *p->step_counter : p->step_index;
-      w = philox4x32_10_rk((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)env,
-                           (uint32_t)(env >> 32) & 0x7FFFFFFFu, rk);
+      StreamKeys ks;
+      make_stream_keys(stream_key(p->seed, idx, env, TAG_STEP), (uint32_t)idx, ks);
+      w = words_from_pair(philox2x32_10_keys((uint32_t)env, ks));
     }
     const bool auto_reset = (p->flags & G2048_FLAG_AUTO_RESET) != 0;
     StepOut o = step_board(lut(), r[0], r[1], r[2], r[3], p->actions[i] & 3u, w, p->max_tile_exp,
@@ -63,7 +63,7 @@ extern "C" int sim_reset(uint8_t* boards, const uint8_t* mask, uint64_t n, uint6
                          uint64_t reset_index) {
   for (uint64_t i = 0; i < n; ++i) {
     if (mask && !mask[i]) continue;
-    Words w = draw_words(seed, base + i, reset_index, 1);
+    Words w = draw_words(seed, base + i, reset_index, TAG_RESET);
     uint32_t r[4];
     fresh_board(lut(), w.w1, w.w2, r[0], r[1], r[2], r[3]);
     store(boards + 16 * i, r);
@@ -75,7 +75,7 @@ extern "C" int sim_add_tile(uint8_t* boards, uint64_t n, uint64_t base, uint64_t
   for (uint64_t i = 0; i < n; ++i) {
     uint32_t r[4];
     load(boards + 16 * i, r);
-    Words w = draw_words(seed, base + i, step_index, 0);
+    Words w = draw_words(seed, base + i, step_index, TAG_STEP);
     spawn(r[0], r[1], r[2], r[3], w.w0);
     store(boards + 16 * i, r);
   }
@@ -123,6 +123,35 @@ extern "C" int sim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_
   return 0;
 }
 
+extern "C" int sim_philox2x32(const uint32_t* ctr, uint32_t key, uint32_t* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    const Pair x = philox2x32_10(ctr[2 * i], ctr[2 * i + 1], key);
+    out[2 * i] = x.x0; out[2 * i + 1] = x.x1;
+  }
+  return 0;
+}
+
+// The three forms the kernels use must agree: draw_words (reset/add_tile/policy kernels, one
+// board at a time), DrawStream (the same with the key cached across boards) and the step
+// kernel's precomputed round keys.  form: 0, 1, 2.
+extern "C" int sim_draw_words(uint32_t* out, uint64_t n, uint64_t base, uint64_t seed, uint64_t idx, uint32_t tag,
+                              int form) {
+  DrawStream ds(seed, idx, tag);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t env = base + i;
+    Words w;
+    if (form == 0) w = draw_words(seed, env, idx, tag);
+    else if (form == 1) w = ds.words(env);
+    else {
+      StreamKeys ks;
+      make_stream_keys(stream_key(seed, idx, env, tag), (uint32_t)idx, ks);
+      w = words_from_pair(philox2x32_10_keys((uint32_t)env, ks));
+    }
+    out[4 * i] = w.w0; out[4 * i + 1] = w.w1; out[4 * i + 2] = w.w2; out[4 * i + 3] = w.w3;
+  }
+  return 0;
+}
+
 extern "C" int sim_symmetry(const uint8_t* in, uint8_t* out, const uint8_t* act_in, uint8_t* act_out, uint64_t n,
                             int hflip, int k) {
   for (uint64_t i = 0; i < n; ++i) {
@@ -143,20 +172,8 @@ extern "C" int sim_symmetry(const uint8_t* in, uint8_t* out, const uint8_t* act_
 extern "C" int sim_sample_actions(const uint8_t* mask, uint8_t* actions, uint64_t n, uint64_t base, uint64_t seed,
                                   uint64_t step_index) {
   for (uint64_t i = 0; i < n; ++i) {
-    Words w = draw_words(seed, base + i, step_index, 0);
-    actions[i] = (uint8_t)pick_action(mask ? mask[i] : 15u, w.w3);
-  }
-  return 0;
-}
-
-extern "C" int sim_philox_head(uint64_t seed, uint64_t idx, const uint64_t* env_ids, uint32_t tag, uint32_t* out, uint64_t n) {
-  RoundKeys rk;
-  make_round_keys(seed, rk);
-  for (uint64_t i = 0; i < n; ++i) {
-    const uint32_t c3 = ((uint32_t)(env_ids[i] >> 32) & 0x7FFFFFFFu) | (tag << 31);
-    const PhiloxHead h = make_philox_head(idx, c3, rk);
-    const Words w = philox4x32_10_head((uint32_t)env_ids[i], h, rk);
-    out[4 * i] = w.w0; out[4 * i + 1] = w.w1; out[4 * i + 2] = w.w2; out[4 * i + 3] = w.w3;
+    Words w = draw_words(seed, base + i, step_index, TAG_POLICY);
+    actions[i] = (uint8_t)pick_action(mask ? mask[i] : 15u, w.w0);
   }
   return 0;
 }

@@ -154,3 +154,21 @@ def check_philox(ops):
     rng = np.random.default_rng(11)
     ctr = rng.integers(0, 2**32, size=(2048, 4), dtype=np.uint64).astype(np.uint32)
     assert np.array_equal(ops.philox(ctr, 5, 9), oracle.philox(ctr, 5, 9))
+    from test_draws import KATS_2X32
+    for ctr2, key, want in KATS_2X32:
+        assert tuple(int(x) for x in ops.philox2x32([ctr2], key)[0]) == want
+    ctr2 = rng.integers(0, 2**32, size=(2048, 2), dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(ops.philox2x32(ctr2, 0xDEADBEEF), oracle.philox2x32(ctr2, 0xDEADBEEF))
+
+
+def check_draw_words(ops):
+    """The draw words of include/g2048.h "Draw stream" for every tag, across a 2^32 env-id
+    boundary and with 64-bit seeds and indices, against the numpy statement of the spec."""
+    from oracle import draws
+    for seed, idx, base in ((0, 0, 0), (42, 5, 1000), (2**64 - 1, 2**64 - 1, 2**32 - 700),
+                            (0x123456789ABCDEF, 2**40 + 7, 2**63 + 2**32 - 3)):
+        for tag in (0, 1, 2):
+            n = 1500
+            env = np.arange(n, dtype=np.uint64) + np.uint64(base)
+            want = draws.draw_words(seed, env, idx, tag)
+            assert np.array_equal(ops.draw_words(n, base, seed, idx, tag), want), (seed, idx, base, tag)

@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), name
     assert sorted(g._lib.EXPORTS) == names
-    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 2
+    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():

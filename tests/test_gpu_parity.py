@@ -22,6 +22,10 @@ def test_philox_on_device(ops):
     pc.check_philox(ops)
 
 
+def test_draw_words_on_device(ops):
+    pc.check_draw_words(ops)
+
+
 def test_shift_table_all_directions(ops):
     pc.check_shift_table_all_directions(ops)
 

@@ -85,20 +85,12 @@ def test_sample_actions_matches_oracle():
         assert np.array_equal(out, oracle.sample_actions(m, n, 123, 42, 17))
 
 
-def test_philox_head_precompute_equals_plain_philox():
-    """The launch-uniform folding of Philox rounds 0-1 (PhiloxHead) gives the Random123 words."""
-    import ctypes as C
-    import numpy as np
-    from backends import sim_lib, _p
-    from oracle import oracle
-    rng = np.random.default_rng(17)
-    n = 4096
-    env = rng.integers(0, 2**63, n, dtype=np.uint64)
-    env[:4] = [0, 1, 2**32 - 1, 2**32]
-    for seed, idx, tag in ((0, 0, 0), (42, 5, 0), (2**64 - 1, 2**64 - 1, 1), (0x123456789ABCDEF, 2**40 + 7, 1)):
-        out = np.zeros((n, 4), np.uint32)
-        sim_lib().sim_philox_head(C.c_uint64(seed), C.c_uint64(idx), _p(env), C.c_uint32(tag), _p(out), C.c_uint64(n))
-        ctr = np.stack([np.full(n, idx & 0xFFFFFFFF, np.uint64), np.full(n, idx >> 32, np.uint64),
-                        env & np.uint64(0xFFFFFFFF), ((env >> np.uint64(32)) & np.uint64(0x7FFFFFFF)) | np.uint64(tag << 31)],
-                       axis=1).astype(np.uint32)
-        assert np.array_equal(out, oracle.philox(ctr, seed & 0xFFFFFFFF, seed >> 32)), (seed, idx, tag)
+def test_draw_words_all_forms():
+    """draw_words, DrawStream (cached key) and the step kernel's precomputed round keys give the
+    words of the spec."""
+    import parity_checks as pc
+
+    for form in (0, 1, 2):
+        class Ops:
+            draw_words = staticmethod(lambda n, base, seed, idx, tag, form=form: SimOps.draw_words(n, base, seed, idx, tag, form))
+        pc.check_draw_words(Ops)
