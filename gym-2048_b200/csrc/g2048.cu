@@ -171,10 +171,57 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
 #define G2048_PTR_INC 0      //    kernel parameters (LDC) and re-deriving the addresses every iteration.  Measured:
 #endif                       //    smem selectors -1.2 %, pointer walk -0.7 %, both together -0.6 % -> selectors only
 
+#ifndef G2048_TMA            // 1: boards and actions reach the SM through a shared-memory ring filled by bulk async
+#define G2048_TMA 0          //    copies (TMA) under mbarriers; 0: per-thread LDG.128 one iteration ahead.
+#endif                       //    Measured (profiles/r01_variants.log): the ring is bit-exact but SLOWER, 15.2 us vs
+                             //    12.4 us per 1 Mi boards with 2 to 5 stages alike — the per-thread loads were never
+                             //    the limiter (the kernel is issue-bound) and the ring's barrier traffic adds ~40
+                             //    instructions per board-warp.  Kept as a tested build variant, not shipped.
+#ifndef G2048_STAGES
+#define G2048_STAGES 4
+#endif
+constexpr int kStages = G2048_STAGES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Bulk async copy global -> shared (TMA, 1-D): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion is signalled as transaction bytes on `bar`.
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <bool EXTRAS, bool COUNTER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
   __shared__ Board4 s_lut[32];
   __shared__ Sel4 s_sel[8];     // [action] = kOrientIn, [4 + action] = kOrientOut
+#if G2048_TMA
+  __shared__ alignas(128) uint4 s_boards[kStages][kThreads];
+  __shared__ alignas(16) uint8_t s_actions[kStages][kThreads];
+  __shared__ alignas(8) uint64_t s_full[kStages], s_empty[kStages];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < kStages; ++k) { mbar_init(&s_full[k], 1u); mbar_init(&s_empty[k], kThreads / 32u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
 #if G2048_PDL
   // Let the next launch in the stream start its ramp as soon as our CTAs retire; everything
   // before griddepcontrol.wait touches no global memory, so it overlaps the previous kernel.
@@ -186,8 +233,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   }
   const Board4* lut = make_reset_lut(s_lut);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
-  const uint32_t n = p.n, stride = gridDim.x * kThreads;
+  const uint32_t n = p.n;
+#if !G2048_TMA
+  const uint32_t stride = gridDim.x * kThreads;
   uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+#endif
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
@@ -199,11 +249,68 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
     dev_idx_lo = (uint32_t)counter_value;
     __syncthreads();                        // every thread of the CTA has read the index before thread 0 can arrive
   }
+#if !G2048_TMA
   if (i >= n) return;
+#endif
   // Grid-stride loop, software-pipelined one board ahead.  orient() consumes the loaded board
   // right away, so the next board is prefetched into the same registers (no rotation copies)
   // a whole iteration before it is used.  (Unrolling by two was measured slower: the doubled
   // body no longer fits the L0 instruction cache; so were two boards per thread.)
+#if G2048_TMA
+  // Staged loop.  The CTA walks tiles of kThreads consecutive boards (tile t = blockIdx.x + k * gridDim.x).  One
+  // elected thread keeps kStages - 1 tiles in flight: per tile two bulk async copies (TMA, cp.async.bulk) bring
+  // the 16-byte boards and the action bytes into a shared-memory ring and complete on the stage's `full`
+  // mbarrier; every thread waits on that barrier, takes its board and action with one LDS.128 and one LDS.U8,
+  // and each warp then arrives on the stage's `empty` barrier, which the producer waits on before it refills
+  // the stage.  Loads are thus decoupled from the registers and run several iterations ahead of the compute.
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_tiles = (n + kThreads - 1u) / kThreads;
+  const bool actions_by_tma = (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0u;
+  auto tile_count = [&](uint32_t t) { const uint32_t left = n - t * kThreads; return left < (uint32_t)kThreads ? left : (uint32_t)kThreads; };
+  auto produce = [&](uint32_t t, uint32_t stage) {      // one thread: arm the barrier, start the copies of tile t
+    const uint32_t cnt = tile_count(t);
+    const bool act_tma = actions_by_tma && (cnt & 15u) == 0u;
+    mbar_expect_tx(&s_full[stage], cnt * 16u + (act_tma ? cnt : 0u));
+    bulk_load(&s_boards[stage][0], p.boards + (size_t)t * kThreads, cnt * 16u, &s_full[stage]);
+    if (act_tma) bulk_load(&s_actions[stage][0], p.actions + (size_t)t * kThreads, cnt, &s_full[stage]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (uint32_t k = 0; k < (uint32_t)kStages - 1u; ++k) {
+      const uint32_t t = blockIdx.x + k * gridDim.x;
+      if (t < n_tiles) produce(t, k);
+    }
+  }
+  uint32_t stage = 0, parity = 0;                 // ring position of iteration k and its use count's parity
+  uint32_t fill_stage = kStages - 1u, fill_parity = 1u;   // where iteration k's refill (tile k + kStages - 1) goes
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t cnt = tile_count(t);
+    const bool act_tma = actions_by_tma && (cnt & 15u) == 0u;
+    const uint32_t i = t * kThreads + tid;
+    const bool valid = tid < cnt;
+    if (tid == 0) {
+      // Refill the stage the CTA consumed in the previous iteration (all warps have normally left it).
+      const uint32_t t_fill = t + ((uint32_t)kStages - 1u) * gridDim.x;
+      if (t_fill < n_tiles && t_fill > t) {
+        mbar_wait(&s_empty[fill_stage], fill_parity);
+        produce(t_fill, fill_stage);
+      }
+    }
+    mbar_wait(&s_full[stage], parity);
+    const uint4 bd = s_boards[stage][tid];
+    uint32_t action = s_actions[stage][tid];
+    if (!act_tma) action = valid ? p.actions[i] : 0u;
+    __syncwarp();
+    if ((tid & 31u) == 0u) mbar_arrive(&s_empty[stage]);
+    const uint32_t act = action & 3u;
+    uint32_t a, b, c, d;
+    orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+    const Sel4 so = s_sel[4u + act];
+    if (valid) step_and_store<EXTRAS, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
+    if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
+    if (++fill_stage == (uint32_t)kStages) { fill_stage = 0; fill_parity ^= 1u; }
+  }
+#else
   const uint4* pb = p.boards + i;
   const uint8_t* pa = p.actions + i;
   uint4 bd = load_board(pb);
@@ -237,6 +344,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
     i = i_next;
   }
+#endif
   // The last CTA to arrive advances the device-side step index: by then every CTA has read it.
   // (Thread 0 of a CTA always owns a board, so it never took the early exit above.)
   if (COUNTER && (p.flags & kFlagBumpCounter) && threadIdx.x == 0) {
@@ -504,6 +612,22 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#endif
+#if G2048_TMA
+  // The staged kernel keeps a shared-memory ring per CTA: ask for a carveout that fits kCtasPerSm of them.
+  {
+    static thread_local int prepared_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != prepared_dev) {
+      const int pct = 50;
+      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      prepared_dev = dev;
+    }
+  }
 #endif
   const bool counter = a->step_counter != nullptr;
   const cudaError_t le =

@@ -88,8 +88,8 @@ def main():
     with open(os.path.join(PROF, "%s_launches_summary.md" % tag), "w") as f:
         f.write("# %s — ncu launch list of `python bench.py --steps 100 --warmup 20` (gpu__time_duration.sum, ns)\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200`; per-launch times are "
-                "cold-cache and serialised.  The timed region of bench.py launches only `g2048_step_kernel<0>`; "
-                "`<1>` and the reset kernel belong to the e2e leg and set-up.\n\n"
+                "cold-cache and serialised.  The timed region of bench.py launches only `g2048_step_kernel<0, 0>` (lean outputs, host-side step index); "
+                "`<1, 0>` and the reset kernel belong to the e2e leg and set-up.\n\n"
                 "| kernel | launches | mean ns | share of listed GPU time |\n|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.0f | %.3f |\n" % (k, len(v), sum(v) / len(v), sum(v) / tot))
