@@ -343,7 +343,7 @@ def run_ours(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "g2048_step_kernel<false>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "g2048_step_kernel<false, false>",
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n,
                      "launch_us": launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,

@@ -241,8 +241,8 @@ class BatchedGame2048:
         return res
 
     def sample_actions(self, legal=False, out=None):
-        """Uniform-random actions for the NEXT step, drawn on the device from word 3 of that
-        step's Philox block (reference: `random.randint(0, 3)`, train.py:119).  legal=True draws
+        """Uniform-random actions for the NEXT step, drawn on the device from the policy-tag draw stream at that
+        step's index (reference: `random.randint(0, 3)`, train.py:119).  legal=True draws
         uniformly among the legal moves of the live boards (needs the `legal_mask` output)."""
         if legal and self.legal_mask is None:
             raise ValueError("sample_actions(legal=True) needs the 'legal_mask' output")

@@ -127,10 +127,11 @@ __device__ __forceinline__ uint4 load_board(const uint4* ptr) {
 // One board, already rotated into its move frame (a,b,c,d), through Game2048Env.step and out to memory.
 // COUNTER: the step index is read from device memory (CUDA-graph replay), so the generator's key
 // and counter word 1 are registers (dev_key, dev_idx_lo) instead of kernel-parameter constants.
+// The finishing half of board i (spawn, score, isend, auto-reset) and its stores; `m` is what the
+// move half (move_oriented) left.
 template <bool EXTRAS, bool COUNTER>
-__device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
-                                               uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
-                                               uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
+__device__ __forceinline__ void finish_and_store(const StepParams& p, const Board4* lut, uint32_t i, const Moved& m,
+                                                 uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
   Words w;
   if (EXTRAS && p.forced_draws) {
     const uint4 f = p.forced_draws[i];
@@ -141,8 +142,8 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
     w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.keys));
   }
   uint4 bd;
-  const StepOut o = step_oriented(lut, a, b, c, d, so, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr,
-                                  auto_reset, bd.x, bd.y, bd.z, bd.w);
+  const StepOut o = finish_step(lut, m, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr, auto_reset, bd.x, bd.y,
+                                bd.z, bd.w);
   p.boards_out[i] = bd;
   p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
   p.dones[i] = o.done ? 1 : 0;
@@ -164,6 +165,21 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
   }
 }
 
+template <bool EXTRAS, bool COUNTER>
+__device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
+                                               uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
+                                               uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
+  finish_and_store<EXTRAS, COUNTER>(p, lut, i, move_oriented(a, b, c, d, so), dev_key, dev_idx_lo, auto_reset);
+}
+
+#ifndef G2048_PIPELINE       // 1: software-pipelined loop — the move half of board j+1 and the finishing half of
+#define G2048_PIPELINE 1     //    board j share one loop body (one straight-line block the scheduler interleaves);
+#endif                       //    -2 % against the plain loop in the same run (profiles/r01_variants_v2.log)
+// Tried on top of this loop and dropped, both bit-exact and both slower because the kernel is issue-bound and every
+// extra instruction costs more than the memory system gives back (same log): warps claiming 32-board tiles from a
+// per-CTA shared-memory counter so that no warp runs out of work early (13.7 us vs 12.4 us: +30 instructions per
+// board-warp for the claim and the ragged-tile predicates), and an L2 bulk prefetch (cp.async.bulk.prefetch.L2) two
+// iterations ahead (13.2 us vs 12.4 us).
 #ifndef G2048_SEL_SMEM       // 1: orientation selectors from shared memory (LDS.128, conflict-free) instead of
 #define G2048_SEL_SMEM 1     //    action-indexed constant memory (a divergent LDC is replayed per distinct address)
 #endif
@@ -309,6 +325,43 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
     if (valid) step_and_store<EXTRAS, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
     if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
     if (++fill_stage == (uint32_t)kStages) { fill_stage = 0; fill_parity ^= 1u; }
+  }
+#elif G2048_PIPELINE
+  // Software-pipelined grid-stride loop.  Iteration j runs the MOVE half of board j+1 (orient, slide+merge,
+  // un-orient: PRMT/LOP3, the ALU pipe) and the FINISHING half of board j (Philox, spawn, float score, isend,
+  // reset, stores: IMAD-heavy, the FMA pipe) as one straight-line block; the two halves are independent, so the
+  // scheduler interleaves them and both pipes stay busy.  Seven registers (Moved) carry a board from one half
+  // to the other.  The board after next is prefetched into the registers orient() has just freed.
+  {
+    uint4 bd = load_board(p.boards + i);
+    uint32_t action = p.actions[i];
+    uint32_t i_next = i + stride;
+    bool more = G2048_PERSISTENT && i_next < n && i_next > i;
+    Moved m;
+    {
+      const uint32_t act = action & 3u;
+      uint32_t a, b, c, d;
+      orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+      const Sel4 so = s_sel[4u + act];
+      if (more) { bd = load_board(p.boards + i_next); action = p.actions[i_next]; }
+      m = move_oriented(a, b, c, d, so);
+    }
+    while (more) {
+      const uint32_t i_cur = i_next;
+      i_next = i_cur + stride;
+      const bool more_next = i_next < n && i_next > i_cur;
+      const uint32_t act = action & 3u;
+      uint32_t a, b, c, d;
+      orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+      const Sel4 so = s_sel[4u + act];
+      if (more_next) { bd = load_board(p.boards + i_next); action = p.actions[i_next]; }
+      const Moved m_next = move_oriented(a, b, c, d, so);
+      finish_and_store<EXTRAS, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
+      m = m_next;
+      i = i_cur;
+      more = more_next;
+    }
+    finish_and_store<EXTRAS, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
   }
 #else
   const uint4* pb = p.boards + i;

@@ -260,8 +260,8 @@ G2048_DEV void compact(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
 template <int K> G2048_DEV float slot_pow2(uint32_t biased) {
   constexpr uint32_t EXPF = 0x7F800000u;
   uint32_t bits;
-  if (K == 3) bits = shr<1>(biased) & EXPF;
-  else if (K == 0) bits = shl<23>(biased);      // only bit 8 of `biased` survives below the field: the sign
+  if constexpr (K == 3) bits = shr<1>(biased) & EXPF;
+  else if constexpr (K == 0) bits = shl<23>(biased);      // only bit 8 of `biased` survives below the field: the sign
   else bits = shl<23 - 8 * K>(biased) & EXPF;
   float f;
 #ifdef G2048_HOST_SIM
@@ -271,14 +271,22 @@ template <int K> G2048_DEV float slot_pow2(uint32_t biased) {
 #endif
   return K == 0 ? __builtin_fabsf(f) : f;       // |x| is an operand modifier of FADD: no instruction
 }
-G2048_DEV float slots_sum(uint32_t slots, uint32_t filled_mask) {
-  const uint32_t biased = addf(slots, filled_mask & L7);     // e + 127 where filled (<= 145: no carry)
+// A slot word (merged exponents, one per byte lane) with the float exponent bias added where the
+// lane holds a merge: e + 127 where filled (<= 145: no carry), 0 elsewhere.
+G2048_DEV uint32_t slots_bias(uint32_t slots, uint32_t filled_mask) { return addf(slots, filled_mask & L7); }
+// Sum of 2^e over the four lanes of a biased slot word.
+G2048_DEV float biased_sum(uint32_t biased) {
   return (slot_pow2<0>(biased) + slot_pow2<1>(biased)) + (slot_pow2<2>(biased) + slot_pow2<3>(biased));
 }
+// The move score (:254) from the two biased slot words of slide_merge_slots: an exact float (a sum
+// of at most 8 powers of two <= 2^18).
+G2048_DEV float slots_score(uint32_t biased_a, uint32_t biased_b) { return biased_sum(biased_a) + biased_sum(biased_b); }
 
-// Slide (a,b,c,d) toward a with merging; returns the move score (:254) as an exact float
-// (a sum of at most 8 powers of two <= 2^18).
-G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+// Slide (a,b,c,d) toward a with merging.  The merged tiles come back as two biased slot words
+// (slots_score turns them into the move score): the step kernel carries those two registers from
+// the move half of one board into the finishing half, which runs an iteration later.
+G2048_DEV void slide_merge_slots(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& biased_a,
+                                 uint32_t& biased_b) {
   compact(a, b, c, d);
   // merges on the compacted line: leftmost pair first, each tile merges once (:252-259)
   //   m1: a==b!=0;  m2: b==c!=0 and not m1;  m3: c==d!=0 and not m2   (bit 7 of each byte)
@@ -297,7 +305,13 @@ G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) 
   // merged exponents: per lane either (m1 and maybe m3) or m2 alone -> two slot words
   const uint32_t sA = (a & M1) | (b & M2);
   const uint32_t sB = cinc & M3;
-  return slots_sum(sA, M1 | M2) + slots_sum(sB, M3);
+  biased_a = slots_bias(sA, M1 | M2);
+  biased_b = slots_bias(sB, M3);
+}
+G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  uint32_t ba, bb;
+  slide_merge_slots(a, b, c, d, ba, bb);
+  return slots_score(ba, bb);
 }
 
 // ---- add_tile (:166-176) under the draw-stream definition ----------------------------
@@ -445,22 +459,40 @@ struct StepOut {
   uint32_t t0, t1, t2, t3;   // post-spawn board (the terminal board when done)
 };
 
-// The step on a board already rotated into the move frame (a,b,c,d) (see orient); `so` is the
-// inverse rotation.  On return r0..r3 hold the board handed back to the agent: the post-spawn
-// board, or a fresh reset() board when the episode ended and auto_reset is set (SB3 DummyVecEnv).
-// Taking the oriented board lets the step kernel reuse the registers of the loaded board for the
-// next board's prefetch as soon as orient() has consumed them.
-G2048_DEV StepOut step_oriented(const Board4* lut, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
-                                const Words& w, uint32_t max_tile_exp, bool want_highest, bool auto_reset,
-                                uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  StepOut o;
+// The step comes in two halves so that the step kernel can run them on DIFFERENT boards in the
+// same loop iteration (software pipelining: the move half is ALU-pipe work — PRMT/LOP3 —, the
+// finishing half FMA-pipe work — Philox, prefix counts, float score; interleaved they keep both
+// pipes busy, one after the other they take turns idling).
+//
+// Move half: a board already rotated into the move frame (a,b,c,d) (see orient; `so` is the
+// inverse rotation) through move() (:194-241).  What the finishing half needs is 7 registers.
+struct Moved {
+  uint32_t r0, r1, r2, r3;     // the moved board, back in row-major order (unchanged when illegal)
+  uint32_t biased_a, biased_b; // merged tiles (slots_score)
+  uint32_t legal;              // 0xFFFFFFFF, or 0 <=> IllegalMove (:238-239): nothing changed
+};
+G2048_DEV Moved move_oriented(uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Sel4 so) {
+  Moved m;
   const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
-  o.score = slide_merge(a, b, c, d);                                                     // :85, :194-241
-  // :238-239 — nothing changed => IllegalMove.  An illegal move leaves (a,b,c,d) as they
-  // were and scores 0, so the same data path serves both cases; only the spawn is gated.
-  o.legal = (((a ^ a0) | (b ^ b0)) | ((c ^ c0) | (d ^ d0))) != 0u;
-  orient(so, a, b, c, d, r0, r1, r2, r3);
-  const uint32_t n_empty = spawn(r0, r1, r2, r3, w.w0, o.legal ? 0xFFFFFFFFu : 0u);     // :88
+  slide_merge_slots(a, b, c, d, m.biased_a, m.biased_b);                                  // :85, :194-241
+  // An illegal move leaves (a,b,c,d) as they were and scores 0, so the same data path serves
+  // both cases; only the spawn is gated.
+  m.legal = ((((a ^ a0) | (b ^ b0)) | ((c ^ c0) | (d ^ d0))) != 0u) ? 0xFFFFFFFFu : 0u;
+  orient(so, a, b, c, d, m.r0, m.r1, m.r2, m.r3);
+  return m;
+}
+
+// Finishing half: spawn, score, isend, auto-reset.  On return r0..r3 hold the board handed back
+// to the agent: the post-spawn board, or a fresh reset() board when the episode ended and
+// auto_reset is set (SB3 DummyVecEnv).
+G2048_DEV StepOut finish_step(const Board4* lut, const Moved& m, const Words& w, uint32_t max_tile_exp,
+                              bool want_highest, bool auto_reset, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                              uint32_t& r3) {
+  StepOut o;
+  o.legal = m.legal != 0u;
+  o.score = slots_score(m.biased_a, m.biased_b);
+  r0 = m.r0; r1 = m.r1; r2 = m.r2; r3 = m.r3;
+  const uint32_t n_empty = spawn(r0, r1, r2, r3, w.w0, m.legal);                         // :88
   o.highest = 0;
   if (want_highest || max_tile_exp != 0u) o.highest = highest_exp(r0, r1, r2, r3);      // :97
   // isend (:262-280) for a legal move; an illegal move terminates (:94)
@@ -470,6 +502,13 @@ G2048_DEV StepOut step_oriented(const Board4* lut, uint32_t a, uint32_t b, uint3
   o.t0 = r0; o.t1 = r1; o.t2 = r2; o.t3 = r3;
   if (auto_reset && o.done) fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);                // :102-111
   return o;
+}
+
+G2048_DEV StepOut step_oriented(const Board4* lut, uint32_t a, uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
+                                const Words& w, uint32_t max_tile_exp, bool want_highest, bool auto_reset,
+                                uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  const Moved m = move_oriented(a, b, c, d, so);
+  return finish_step(lut, m, w, max_tile_exp, want_highest, auto_reset, r0, r1, r2, r3);
 }
 
 G2048_DEV StepOut step_board(const Board4* lut, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,

@@ -10,22 +10,11 @@
 
 using namespace g2048;
 
-enum Mode { FULL = 0, MEM_ONLY = 1, NO_PHILOX = 2, NO_SPAWN = 3, NO_MOVE = 4, NO_SCORE = 5, PHILOX_ONLY = 6, NO_LOADS = 7, P2X32 = 8, PSHARE4 = 9 };
-
-// Philox2x32-10 (Random123): what the step would cost with the narrower generator (experiment only)
-__device__ __forceinline__ Words philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
-    c0 = hi ^ key ^ c1; c1 = lo; key += 0x9E3779B9u;
-  }
-  return Words{c0, c1, c1 * 0x9E3779B9u, 0};
-}
-
+enum Mode { FULL = 0, MEM_ONLY = 1, NO_PHILOX = 2, NO_SPAWN = 3, NO_MOVE = 4, NO_SCORE = 5, PHILOX_ONLY = 6, NO_LOADS = 7 };
 
 struct P {
   uint4* boards; const uint8_t* actions; float* rewards; uint8_t* dones;
-  uint32_t n; uint64_t step_index; RoundKeys rk;
+  uint32_t n; uint64_t step_index; StreamKeys keys;
 };
 
 template <int MODE, int THREADS, int CTAS>
@@ -41,8 +30,6 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
   uint4 bd; uint32_t action;
   if (MODE == NO_LOADS) { bd = make_uint4(i * 0x01010101u & 0x03030303u, 0x01020102u, i & 0x07070707u, 0x00010203u); action = i; }
   else { bd = p.boards[i]; action = p.actions[i]; }
-  Words wq = Words{0, 0, 0, 0};
-  uint32_t it = 0;
   while (true) {
     const uint32_t i_next = i + stride;
     const bool more = i_next < n;
@@ -52,15 +39,8 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
       else { bd_next = p.boards[i_next]; action_next = p.actions[i_next]; }
     }
     Words w;
-    if (MODE == P2X32) { w = philox2x32_10(i, (uint32_t)p.step_index, p.rk.k0[0]); }
-    else if (MODE == PSHARE4) {
-      // one Philox4x32 block per 4 iterations of this thread, words rotated (cost model of block sharing)
-      if ((it & 3u) == 0u) wq = philox4x32_10_rk((uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), i, 0u, p.rk);
-      else { const uint32_t t = wq.w0; wq.w0 = wq.w1; wq.w1 = wq.w2; wq.w2 = wq.w3; wq.w3 = t; }
-      w = wq;
-    }
-    else if (MODE == NO_PHILOX || MODE == MEM_ONLY) { w = Words{i * 0x9E3779B9u ^ (uint32_t)p.step_index, i * 0x85EBCA6Bu, i * 0xC2B2AE35u, 0}; }
-    else w = philox4x32_10_rk((uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), i, 0u, p.rk);
+    if (MODE == NO_PHILOX || MODE == MEM_ONLY) { w = Words{i * 0x9E3779B9u ^ (uint32_t)p.step_index, i * 0x85EBCA6Bu, i * 0xC2B2AE35u, 0}; }
+    else w = words_from_pair(philox2x32_10_keys(i, p.keys));
     float reward; bool done;
     if (MODE == MEM_ONLY) {
       bd.x ^= action; reward = (float)(bd.y & 0xFF); done = (bd.z & 1u) != 0u;
@@ -89,7 +69,6 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
       p.boards[i] = bd; p.rewards[i] = reward; p.dones[i] = done ? 1 : 0;
     }
     if (!more) break;
-    ++it;
     i = i_next; bd = bd_next; action = action_next;
   }
 }
@@ -99,7 +78,7 @@ double time_mode(const char* name, uint32_t n, int sets, int steps, std::vector<
                  float* rewards, uint8_t* dones, bool pdl) {
   int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   P p; p.actions = actions; p.rewards = rewards; p.dones = dones; p.n = n;
-  make_round_keys(42, p.rk);
+
   cudaLaunchConfig_t cfg = {};
   unsigned need = (n + THREADS - 1) / THREADS, cap = sms * CTAS;
   cfg.gridDim = dim3(need < cap ? need : cap); cfg.blockDim = dim3(THREADS);
@@ -110,9 +89,9 @@ double time_mode(const char* name, uint32_t n, int sets, int steps, std::vector<
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   double best = 1e30;
   for (int rep = 0; rep < 3; ++rep) {
-    for (int t = 0; t < 20; ++t) { p.boards = boards[t % sets]; p.step_index = t; p.actions = actions + (n <= (1u << 20) ? (size_t)(t % 8) << 20 : 0); cudaLaunchKernelEx(&cfg, k<MODE, THREADS, CTAS>, p); }
+    for (int t = 0; t < 20; ++t) { p.boards = boards[t % sets]; p.step_index = t; make_stream_keys(stream_key(42, t, 0, 0), t, p.keys); p.actions = actions + (n <= (1u << 20) ? (size_t)(t % 8) << 20 : 0); cudaLaunchKernelEx(&cfg, k<MODE, THREADS, CTAS>, p); }
     cudaEventRecord(e0);
-    for (int t = 0; t < steps; ++t) { p.boards = boards[t % sets]; p.step_index = 100 + t; p.actions = actions + (n <= (1u << 20) ? (size_t)(t % 8) << 20 : 0); cudaLaunchKernelEx(&cfg, k<MODE, THREADS, CTAS>, p); }
+    for (int t = 0; t < steps; ++t) { p.boards = boards[t % sets]; p.step_index = 100 + t; make_stream_keys(stream_key(42, 100 + t, 0, 0), 100 + t, p.keys); p.actions = actions + (n <= (1u << 20) ? (size_t)(t % 8) << 20 : 0); cudaLaunchKernelEx(&cfg, k<MODE, THREADS, CTAS>, p); }
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double us = ms * 1e3 / steps;
@@ -152,7 +131,7 @@ int main(int argc, char** argv) {
   printf("== ablations at 1 Mi boards, 8 sets (HBM), 512x2, PDL\n");
   RUN(FULL, 512, 2, 8, true); RUN(MEM_ONLY, 512, 2, 8, true); RUN(NO_PHILOX, 512, 2, 8, true); RUN(NO_SPAWN, 512, 2, 8, true);
   RUN(NO_MOVE, 512, 2, 8, true); RUN(NO_SCORE, 512, 2, 8, true); RUN(PHILOX_ONLY, 512, 2, 8, true); RUN(NO_LOADS, 512, 2, 8, true);
-  RUN(P2X32, 512, 2, 8, true); RUN(PSHARE4, 512, 2, 8, true); RUN(FULL, 512, 2, 8, true);
+  RUN(FULL, 512, 2, 8, true);
   if (argc > 1) return 0;
   printf("== 1 set (L2 resident)\n");
   RUN(FULL, 512, 2, 1, true); RUN(MEM_ONLY, 512, 2, 1, true);

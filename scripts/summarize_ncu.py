@@ -86,7 +86,7 @@ def main():
             agg[r[kn]].append(float(r[mv].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(PROF, "%s_launches_summary.md" % tag), "w") as f:
-        f.write("# %s — ncu launch list of `python bench.py --steps 100 --warmup 20` (gpu__time_duration.sum, ns)\n\n"
+        f.write("# " + tag + " — ncu launch list of `python bench.py --steps 100 --warmup 20` (gpu__time_duration.sum, ns)\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200`; per-launch times are "
                 "cold-cache and serialised.  The timed region of bench.py launches only `g2048_step_kernel<0, 0>` (lean outputs, host-side step index); "
                 "`<1, 0>` and the reset kernel belong to the e2e leg and set-up.\n\n"
