@@ -50,6 +50,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 #ifndef G2048_PERSISTENT     // 1: grid-stride loop over a grid sized to the SM count; 0: one board per thread
 #define G2048_PERSISTENT 1
 #endif
+#ifndef G2048_TMA            // 1: boards and actions reach the SM through a shared-memory ring filled by bulk async
+#define G2048_TMA 0          //    copies (TMA) under mbarriers; 0: per-thread LDG.128 one iteration ahead.
+#endif                       //    Measured (profiles/r01_variants.log): the ring is bit-exact but SLOWER, 15.2 us vs
+                             //    12.4 us per 1 Mi boards with 2 to 5 stages alike — the per-thread loads were never
+                             //    the limiter (the kernel is issue-bound) and the ring's barrier traffic adds ~40
+                             //    instructions per board-warp.  Kept as a tested build variant, not shipped.
+#ifndef G2048_STAGES
+#define G2048_STAGES 4
+#endif
 constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");
 
@@ -100,6 +109,27 @@ struct StepParams {
   uint32_t flags;
 };
 
+// The 1024 fresh boards of two_tile_board() (g2048_device.cuh), built at compile time: the step kernel
+// brings the table into shared memory with ONE bulk async copy (TMA) per CTA, issued before
+// griddepcontrol.wait — it is constant data, so the copy overlaps the previous launch's tail — instead of
+// spending ~60 instructions per thread rebuilding it every launch.
+struct alignas(128) PairLut { Board4 e[1024]; };
+constexpr Board4 one_tile_board_c(uint32_t entry) {
+  const uint32_t cell = entry >> 1, v = ((entry & 1u) + 1u) << ((cell & 3u) * 8u), row = cell >> 2;
+  return Board4{row == 0 ? v : 0u, row == 1 ? v : 0u, row == 2 ? v : 0u, row == 3 ? v : 0u};
+}
+constexpr PairLut make_pair_lut() {
+  PairLut t{};
+  for (uint32_t entry = 0; entry < 1024u; ++entry) {
+    const uint32_t k1 = entry >> 6, k2r = (entry >> 2) & 15u, t1 = (entry >> 1) & 1u, t2 = entry & 1u;
+    const uint32_t k2 = (k2r + ((k2r >= k1) ? 1u : 0u)) & 15u;
+    const Board4 b1 = one_tile_board_c(2u * k1 + t1), b2 = one_tile_board_c(2u * k2 + t2);
+    t.e[entry] = Board4{b1.x | b2.x, b1.y | b2.y, b1.z | b2.z, b1.w | b2.w};
+  }
+  return t;
+}
+__device__ const PairLut g_pair_lut = make_pair_lut();
+
 // Game2048Env.step (:76-100) for n boards.  EXTRAS=false is the lean variant used when
 // none of the optional outputs/inputs is requested (boards, actions, rewards, dones only).
 // The 32 one-tile boards fresh_board() ORs together, built once per CTA in shared memory.
@@ -127,6 +157,9 @@ __device__ __forceinline__ uint4 load_board(const uint4* ptr) {
 // One board, already rotated into its move frame (a,b,c,d), through Game2048Env.step and out to memory.
 // COUNTER: the step index is read from device memory (CUDA-graph replay), so the generator's key
 // and counter word 1 are registers (dev_key, dev_idx_lo) instead of kernel-parameter constants.
+#ifndef G2048_PAIR_LUT       // 1: the step kernel's reset path reads whole fresh boards from a 16 KB shared-memory
+#define G2048_PAIR_LUT 1     //    table (two_tile_board) instead of OR-ing two entries of the 32-entry one-tile table
+#endif
 // The finishing half of board i (spawn, score, isend, auto-reset) and its stores; `m` is what the
 // move half (move_oriented) left.
 template <bool EXTRAS, bool COUNTER>
@@ -142,8 +175,8 @@ __device__ __forceinline__ void finish_and_store(const StepParams& p, const Boar
     w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.keys));
   }
   uint4 bd;
-  const StepOut o = finish_step(lut, m, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr, auto_reset, bd.x, bd.y,
-                                bd.z, bd.w);
+  const StepOut o = finish_step<(G2048_PAIR_LUT && !G2048_TMA)>(lut, m, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr,
+                                                    auto_reset, bd.x, bd.y, bd.z, bd.w);
   p.boards_out[i] = bd;
   p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
   p.dones[i] = o.done ? 1 : 0;
@@ -187,15 +220,6 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
 #define G2048_PTR_INC 0      //    kernel parameters (LDC) and re-deriving the addresses every iteration.  Measured:
 #endif                       //    smem selectors -1.2 %, pointer walk -0.7 %, both together -0.6 % -> selectors only
 
-#ifndef G2048_TMA            // 1: boards and actions reach the SM through a shared-memory ring filled by bulk async
-#define G2048_TMA 0          //    copies (TMA) under mbarriers; 0: per-thread LDG.128 one iteration ahead.
-#endif                       //    Measured (profiles/r01_variants.log): the ring is bit-exact but SLOWER, 15.2 us vs
-                             //    12.4 us per 1 Mi boards with 2 to 5 stages alike — the per-thread loads were never
-                             //    the limiter (the kernel is issue-bound) and the ring's barrier traffic adds ~40
-                             //    instructions per board-warp.  Kept as a tested build variant, not shipped.
-#ifndef G2048_STAGES
-#define G2048_STAGES 4
-#endif
 constexpr int kStages = G2048_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -226,7 +250,18 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 
 template <bool EXTRAS, bool COUNTER>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
+#if G2048_PAIR_LUT && !G2048_TMA
+  __shared__ alignas(128) Board4 s_lut[1024];
+  __shared__ alignas(8) uint64_t s_lut_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_lut_bar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s_lut_bar, (uint32_t)sizeof(PairLut));
+    bulk_load(s_lut, &g_pair_lut, (uint32_t)sizeof(PairLut), &s_lut_bar);
+  }
+#else
   __shared__ Board4 s_lut[32];
+#endif
   __shared__ Sel4 s_sel[8];     // [action] = kOrientIn, [4 + action] = kOrientOut
 #if G2048_TMA
   __shared__ alignas(128) uint4 s_boards[kStages][kThreads];
@@ -247,7 +282,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
     const uint32_t k = threadIdx.x - 32;
     s_sel[k] = (k < 4) ? kOrientIn[k] : kOrientOut[k - 4];
   }
+#if G2048_PAIR_LUT && !G2048_TMA
+  __syncthreads();                          // s_sel written, s_lut_bar initialised
+  const Board4* lut = s_lut;
+#else
   const Board4* lut = make_reset_lut(s_lut);
+#endif
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
   const uint32_t n = p.n;
 #if !G2048_TMA
@@ -256,6 +296,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+#if G2048_PAIR_LUT && !G2048_TMA
+  mbar_wait(&s_lut_bar, 0u);                // the table copy was started in the prologue; long done by now
 #endif
   uint64_t counter_value = 0;
   uint32_t dev_key = 0u, dev_idx_lo = 0u;

@@ -340,11 +340,19 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
   // (tile 2, exponent 1) or 6 (tile 4, exponent 2) gives the tile byte; the cell is empty, so adding
   // equals inserting.  The shift is the high half of t_i * 2^25 / 2^26: one IMAD.HI per row, and a
   // zero multiplier (illegal move: no tile, :91-95) disables the spawn.
+#if defined(G2048_SPREAD_INSERT) && G2048_SPREAD_INSERT
+  const uint32_t tile = ((f < P2_THRESHOLD) ? K1 : 2u * K1) & enable;                             // :168
+  r0 |= spread(addf(p0, gk) & ~addf(p0, gk1) & e0) & tile;
+  r1 |= spread(addf(p1, gk) & ~addf(p1, gk1) & e1) & tile;
+  r2 |= spread(addf(p2, gk) & ~addf(p2, gk1) & e2) & tile;
+  r3 |= spread(addf(p3, gk) & ~addf(p3, gk1) & e3) & tile;
+#else
   const uint32_t mult = ((f < P2_THRESHOLD) ? (1u << 25) : (1u << 26)) & enable;                  // :168
   r0 = madhi(addf(p0, gk) & ~addf(p0, gk1) & e0, mult, r0);
   r1 = madhi(addf(p1, gk) & ~addf(p1, gk1) & e1, mult, r1);
   r2 = madhi(addf(p2, gk) & ~addf(p2, gk1) & e2, mult, r2);
   r3 = madhi(addf(p3, gk) & ~addf(p3, gk1) & e3, mult, r3);
+#endif
   return n;
 }
 
@@ -366,6 +374,26 @@ G2048_DEV void fresh_board(const Board4* lut, uint32_t w1, uint32_t w2, uint32_t
   const uint32_t i2 = 2u * k2 + (((w2 * 15u) < P2_THRESHOLD) ? 0u : 1u);
   const Board4 t1 = lut[i1], t2 = lut[i2];
   r0 = t1.x | t2.x; r1 = t1.y | t2.y; r2 = t1.z | t2.z; r3 = t1.w | t2.w;
+}
+
+// The same through a table of whole fresh boards, one per outcome of the two spawns: entry
+// k1*64 + k2r*4 + t1*2 + t2, k1 = cell of the first tile, k2r = rank of the second tile's cell among
+// the 15 cells left (the table builder skips k1), t = 1 for a 4.  1024 entries (k2r = 15 unused),
+// 16 KB of shared memory: half the instructions of fresh_board in the reset path of the step kernel.
+G2048_DEV Board4 two_tile_board(uint32_t entry) {
+  const uint32_t k1 = entry >> 6, k2r = (entry >> 2) & 15u, t1 = (entry >> 1) & 1u, t2 = entry & 1u;
+  const uint32_t k2 = (k2r + ((k2r >= k1) ? 1u : 0u)) & 15u;
+  const Board4 b1 = one_tile_board(2u * k1 + t1), b2 = one_tile_board(2u * k2 + t2);
+  return Board4{b1.x | b2.x, b1.y | b2.y, b1.z | b2.z, b1.w | b2.w};
+}
+G2048_DEV void fresh_board_pairs(const Board4* pair_lut, uint32_t w1, uint32_t w2, uint32_t& r0, uint32_t& r1,
+                                 uint32_t& r2, uint32_t& r3) {
+  const uint32_t k1 = w1 >> 28;
+  const uint32_t t1 = (shl<4>(w1) < P2_THRESHOLD) ? 0u : 2u;
+  const uint32_t k2r = __umulhi(w2, 15u);
+  const uint32_t t2 = ((w2 * 15u) < P2_THRESHOLD) ? 0u : 1u;
+  const Board4 b = pair_lut[k1 * 64u + k2r * 4u + t1 + t2];
+  r0 = b.x; r1 = b.y; r2 = b.z; r3 = b.w;
 }
 
 // ---- board queries --------------------------------------------------------------------
@@ -485,6 +513,7 @@ G2048_DEV Moved move_oriented(uint32_t a, uint32_t b, uint32_t c, uint32_t d, co
 // Finishing half: spawn, score, isend, auto-reset.  On return r0..r3 hold the board handed back
 // to the agent: the post-spawn board, or a fresh reset() board when the episode ended and
 // auto_reset is set (SB3 DummyVecEnv).
+template <bool PAIR_LUT = false>
 G2048_DEV StepOut finish_step(const Board4* lut, const Moved& m, const Words& w, uint32_t max_tile_exp,
                               bool want_highest, bool auto_reset, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                               uint32_t& r3) {
@@ -500,7 +529,10 @@ G2048_DEV StepOut finish_step(const Board4* lut, const Moved& m, const Words& w,
   if (max_tile_exp != 0u) end = end || (o.highest == max_tile_exp);                      // :267
   o.done = end || !o.legal;
   o.t0 = r0; o.t1 = r1; o.t2 = r2; o.t3 = r3;
-  if (auto_reset && o.done) fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);                // :102-111
+  if (auto_reset && o.done) {                                                            // :102-111
+    if (PAIR_LUT) fresh_board_pairs(lut, w.w1, w.w2, r0, r1, r2, r3);
+    else fresh_board(lut, w.w1, w.w2, r0, r1, r2, r3);
+  }
   return o;
 }
 
