@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
 #if G2048_PDL
   // Let the next launch in the stream start its ramp as soon as our CTAs retire; everything
-  // before griddepcontrol.wait touches no global memory, so it overlaps the previous kernel.
+  // before griddepcontrol.wait touches no global memory a previous launch could have written (only the
+  // constant fresh-board table), so it overlaps the previous kernel.
   asm volatile("griddepcontrol.launch_dependents;");
 #endif
   if (threadIdx.x >= 32 && threadIdx.x < 40) {
