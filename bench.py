@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--sets", type=int, default=8)
     ap.add_argument("--action-pool", type=int, default=16)
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=3)
     ap.add_argument("--ref-steps-per-proc", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -376,7 +376,7 @@ class HostSteppedEnv:
         cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
                              int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
                              int(n_chunks), 0)
-        self._n_chunks = min(int(n_chunks) if n_chunks else 4, 64)
+        self._n_chunks = min(int(n_chunks) if n_chunks else 3, 64)
         self._h = C.c_void_p()
         check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
         self.buffers = HostBuffers(self.num_envs, extras)
@@ -408,10 +408,15 @@ class HostSteppedEnv:
 
     @property
     def n_chunks_effective(self):
-        """Kernel launches per step_host call (the library rounds slices up to 256 boards)."""
-        per = -(-self.num_envs // self._n_chunks)
+        """Kernel launches per step_host call: the library's slice schedule (g2048_env_step_host) — a lead
+        slice of 1/16 of the boards when there are at least two slices and 65,536 boards, the rest in equal
+        slices, every slice rounded up to 256 boards."""
+        n, chunks = self.num_envs, self._n_chunks
+        lead = -(-(n // 16) // 256) * 256 if (chunks >= 2 and n >= 65536) else 0
+        rest = chunks - 1 if lead else chunks
+        per = -(-(n - lead) // rest)
         per = -(-per // 256) * 256
-        return -(-self.num_envs // per)
+        return (1 if lead else 0) + -(-(n - lead) // per)
 
     @property
     def step_index(self):

@@ -285,7 +285,7 @@ typedef struct G2048EnvConfig {
   uint64_t seed;
   float    illegal_move_reward;
   uint32_t max_tile_exp;
-  uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default */
+  uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default (3: a 1/16 lead slice + 2) */
   uint32_t reserved;
 } G2048EnvConfig;
 
