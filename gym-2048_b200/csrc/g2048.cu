@@ -520,48 +520,57 @@ g2048_status_kernel(const uint4* boards, uint8_t* lm, uint8_t* hi, uint8_t* ne, 
   }
 }
 
-// stack() (:17-32): obs[n][16][4][4]; one thread per (board, channel, row) writes the four
-// cells of that row, so consecutive threads write consecutive addresses for every dtype.
-template <typename T> struct Obs4;
-template <> struct Obs4<uint8_t> {
-  static __device__ __forceinline__ void store(uint8_t* o, uint64_t t, uint32_t f) {   // f: 0/1 per byte
-    reinterpret_cast<uint32_t*>(o)[t] = f;
+// stack() (:17-32): obs[n][16][4][4].  The output is cut into 16-byte chunks and every thread writes exactly
+// one of them with one 128-bit store, consecutive threads consecutive chunks (512 contiguous bytes per warp
+// instruction) whatever the dtype:
+//   u8   16 chunks per board: a whole channel (16 cells)     bf16 32: two rows of a channel (8 cells)
+//   f32  64: one row of a channel (4 cells)                  i64 128: half a row (2 cells)
+// The board rows a chunk needs are re-read through L1 (16 to 128 threads share a board).
+// eq_flags(r, ch): 0/1 per byte, 1 where the cell holds exponent ch (exponents >= 16 match no channel,
+// :28-30; ch 0 = empty, :25).
+__device__ __forceinline__ uint32_t eq_flags(uint32_t r, uint32_t ch) { return (~((r ^ (ch * K1)) + L7) & H) >> 7; }
+struct bf16x4 { uint32_t lo, hi; };   // tag type of the bf16 encoder
+template <typename T> struct ObsChunk;
+template <> struct ObsChunk<uint8_t> {
+  static constexpr uint32_t kPerBoardLog2 = 4;
+  static __device__ __forceinline__ uint4 make(const uint32_t* board, uint32_t c) {
+    const uint4 b = *reinterpret_cast<const uint4*>(board);
+    return make_uint4(eq_flags(b.x, c), eq_flags(b.y, c), eq_flags(b.z, c), eq_flags(b.w, c));
   }
 };
-template <> struct Obs4<float> {
-  static __device__ __forceinline__ void store(float* o, uint64_t t, uint32_t f) {
-    reinterpret_cast<float4*>(o)[t] = make_float4((float)(f & 1u), (float)((f >> 8) & 1u),
-                                                  (float)((f >> 16) & 1u), (float)(f >> 24));
+template <> struct ObsChunk<bf16x4> {
+  static constexpr uint32_t kPerBoardLog2 = 5;
+  static __device__ __forceinline__ uint32_t pair(uint32_t f) {       // two 0/1 bytes -> two bf16 (1.0 = 0x3F80)
+    return ((f & 1u) * 0x3F80u) | (((f >> 8) & 1u) * 0x3F800000u);
+  }
+  static __device__ __forceinline__ uint4 make(const uint32_t* board, uint32_t c) {
+    const uint2 r = *reinterpret_cast<const uint2*>(board + 2u * (c & 1u));
+    const uint32_t f0 = eq_flags(r.x, c >> 1), f1 = eq_flags(r.y, c >> 1);
+    return make_uint4(pair(f0), pair(f0 >> 16), pair(f1), pair(f1 >> 16));
   }
 };
-template <> struct Obs4<int64_t> {
-  static __device__ __forceinline__ void store(int64_t* o, uint64_t t, uint32_t f) {
-    longlong2* q = reinterpret_cast<longlong2*>(o) + 2 * t;
-    q[0] = make_longlong2((long long)(f & 1u), (long long)((f >> 8) & 1u));
-    q[1] = make_longlong2((long long)((f >> 16) & 1u), (long long)(f >> 24));
+template <> struct ObsChunk<float> {
+  static constexpr uint32_t kPerBoardLog2 = 6;
+  static __device__ __forceinline__ uint4 make(const uint32_t* board, uint32_t c) {
+    const uint32_t f = eq_flags(board[c & 3u], c >> 2);
+    constexpr uint32_t one = 0x3F800000u;
+    return make_uint4((f & 1u) * one, ((f >> 8) & 1u) * one, ((f >> 16) & 1u) * one, (f >> 24) * one);
   }
 };
-struct bf16x4 { uint32_t lo, hi; };
-template <> struct Obs4<bf16x4> {
-  static __device__ __forceinline__ void store(bf16x4* o, uint64_t t, uint32_t f) {   // bf16 1.0 = 0x3F80
-    uint2 v;
-    v.x = ((f & 1u) * 0x3F80u) | (((f >> 8) & 1u) * 0x3F800000u);
-    v.y = (((f >> 16) & 1u) * 0x3F80u) | ((f >> 24) * 0x3F800000u);
-    reinterpret_cast<uint2*>(o)[t] = v;
+template <> struct ObsChunk<int64_t> {
+  static constexpr uint32_t kPerBoardLog2 = 7;
+  static __device__ __forceinline__ uint4 make(const uint32_t* board, uint32_t c) {
+    const uint32_t f = eq_flags(board[(c >> 1) & 3u], c >> 3) >> (16u * (c & 1u));
+    return make_uint4(f & 1u, 0u, (f >> 8) & 1u, 0u);
   }
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) g2048_obs_kernel(const uint32_t* boards, T* obs, uint64_t n_rows64) {
-  // t enumerates (board, channel, row): board = t / 64, channel = (t / 4) % 16, row = t % 4
+__global__ void __launch_bounds__(kThreads) g2048_obs_kernel(const uint32_t* boards, uint4* obs, uint64_t n_chunks) {
+  constexpr uint32_t kLog2 = ObsChunk<T>::kPerBoardLog2;
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-  for (uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x; t < n_rows64; t += stride) {
-    const uint32_t row = (uint32_t)t & 3u, ch = ((uint32_t)t >> 2) & 15u;
-    const uint32_t r = boards[(t >> 6) * 4 + row];
-    // byte == ch (exponents >= 16 match no channel, :28-30; ch 0 = empty, :25)
-    const uint32_t eq = (~((r ^ (ch * K1)) + L7) & H) >> 7;
-    Obs4<T>::store(obs, t, eq);
-  }
+  for (uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x; t < n_chunks; t += stride)
+    obs[t] = ObsChunk<T>::make(boards + (t >> kLog2) * 4u, (uint32_t)t & ((1u << kLog2) - 1u));
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -573,18 +582,42 @@ g2048_values_from_exp_kernel(const uint8_t* exps, int64_t* values, uint64_t n_ce
   }
 }
 
+// The same four cells (one board row) per thread: one 32-bit load, two 128-bit stores.
+__global__ void __launch_bounds__(kThreads)
+g2048_values_from_exp4_kernel(const uint32_t* rows, longlong2* values, uint64_t n_rows) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_rows; i += stride) {
+    const uint32_t r = rows[i];
+    auto val = [](uint32_t e) { return e ? (long long)(1ull << (e & 63u)) : 0ll; };
+    values[2 * i] = make_longlong2(val(r & 0xFFu), val((r >> 8) & 0xFFu));
+    values[2 * i + 1] = make_longlong2(val((r >> 16) & 0xFFu), val(r >> 24));
+  }
+}
+
+__device__ __forceinline__ uint32_t exp_of_value(int64_t v, uint32_t* bad_count) {
+  uint32_t e = 0;
+  if (v != 0) {
+    const bool ok = v >= 2 && v <= (1ll << 31) && (v & (v - 1)) == 0;
+    if (ok) e = 63u - (uint32_t)__clzll(v);
+    else if (bad_count) atomicAdd(bad_count, 1u);
+  }
+  return e;
+}
+__global__ void __launch_bounds__(kThreads)
+g2048_exp_from_values4_kernel(const longlong2* values, uint32_t* rows, uint64_t n_rows, uint32_t* bad_count) {
+  const uint64_t stride = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_rows; i += stride) {
+    const longlong2 a = values[2 * i], b = values[2 * i + 1];
+    rows[i] = exp_of_value(a.x, bad_count) | (exp_of_value(a.y, bad_count) << 8) |
+              (exp_of_value(b.x, bad_count) << 16) | (exp_of_value(b.y, bad_count) << 24);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 g2048_exp_from_values_kernel(const int64_t* values, uint8_t* exps, uint64_t n_cells, uint32_t* bad_count) {
   const uint64_t stride = (uint64_t)gridDim.x * kThreads;
   for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < n_cells; i += stride) {
-    const int64_t v = values[i];
-    uint32_t e = 0;
-    if (v != 0) {
-      const bool ok = v >= 2 && v <= (1ll << 31) && (v & (v - 1)) == 0;
-      if (ok) e = 63u - (uint32_t)__clzll(v);
-      else if (bad_count) atomicAdd(bad_count, 1u);
-    }
-    exps[i] = (uint8_t)e;
+    exps[i] = (uint8_t)exp_of_value(values[i], bad_count);
   }
 }
 
@@ -810,14 +843,14 @@ int g2048_encode_obs(const uint8_t* boards, void* obs, int dtype, uint64_t n, vo
   if (!boards || !obs) return fail(G2048_ERR_INVALID, "g2048_encode_obs: boards and obs are required");
   if (!aligned16(boards) || !aligned16(obs))
     return fail(G2048_ERR_ALIGN, "g2048_encode_obs: boards and obs must be 16-byte aligned");
-  const uint64_t t = n * 64;
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   const uint32_t* b = reinterpret_cast<const uint32_t*>(boards);
+  uint4* o = static_cast<uint4*>(obs);
   switch (dtype) {
-    case G2048_OBS_U8:   g2048_obs_kernel<uint8_t><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<uint8_t*>(obs), t); break;
-    case G2048_OBS_F32:  g2048_obs_kernel<float><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<float*>(obs), t); break;
-    case G2048_OBS_I64:  g2048_obs_kernel<int64_t><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<int64_t*>(obs), t); break;
-    case G2048_OBS_BF16: g2048_obs_kernel<bf16x4><<<grid_for(t), kThreads, 0, s>>>(b, static_cast<bf16x4*>(obs), t); break;
+    case G2048_OBS_U8:   g2048_obs_kernel<uint8_t><<<grid_for(n << 4), kThreads, 0, s>>>(b, o, n << 4); break;
+    case G2048_OBS_BF16: g2048_obs_kernel<bf16x4><<<grid_for(n << 5), kThreads, 0, s>>>(b, o, n << 5); break;
+    case G2048_OBS_F32:  g2048_obs_kernel<float><<<grid_for(n << 6), kThreads, 0, s>>>(b, o, n << 6); break;
+    case G2048_OBS_I64:  g2048_obs_kernel<int64_t><<<grid_for(n << 7), kThreads, 0, s>>>(b, o, n << 7); break;
     default: return fail(G2048_ERR_INVALID, "g2048_encode_obs: unknown dtype %d", dtype);
   }
   return launch_check("g2048_obs_kernel");
@@ -826,8 +859,12 @@ int g2048_encode_obs(const uint8_t* boards, void* obs, int dtype, uint64_t n, vo
 int g2048_values_from_exp(const uint8_t* boards, int64_t* values, uint64_t n_cells, void* stream) {
   if (n_cells == 0) return G2048_OK;
   if (!boards || !values) return fail(G2048_ERR_INVALID, "g2048_values_from_exp: NULL pointer");
-  g2048_values_from_exp_kernel<<<grid_for(n_cells), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      boards, values, n_cells);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((n_cells & 3u) == 0 && (reinterpret_cast<uintptr_t>(boards) & 3u) == 0 && aligned16(values))   // whole rows
+    g2048_values_from_exp4_kernel<<<grid_for(n_cells / 4), kThreads, 0, s>>>(
+        reinterpret_cast<const uint32_t*>(boards), reinterpret_cast<longlong2*>(values), n_cells / 4);
+  else
+    g2048_values_from_exp_kernel<<<grid_for(n_cells), kThreads, 0, s>>>(boards, values, n_cells);
   return launch_check("g2048_values_from_exp_kernel");
 }
 
@@ -835,8 +872,12 @@ int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cel
                           void* stream) {
   if (n_cells == 0) return G2048_OK;
   if (!boards || !values) return fail(G2048_ERR_INVALID, "g2048_exp_from_values: NULL pointer");
-  g2048_exp_from_values_kernel<<<grid_for(n_cells), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      values, boards, n_cells, bad_count);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((n_cells & 3u) == 0 && (reinterpret_cast<uintptr_t>(boards) & 3u) == 0 && aligned16(values))   // whole rows
+    g2048_exp_from_values4_kernel<<<grid_for(n_cells / 4), kThreads, 0, s>>>(
+        reinterpret_cast<const longlong2*>(values), reinterpret_cast<uint32_t*>(boards), n_cells / 4, bad_count);
+  else
+    g2048_exp_from_values_kernel<<<grid_for(n_cells), kThreads, 0, s>>>(values, boards, n_cells, bad_count);
   return launch_check("g2048_exp_from_values_kernel");
 }
 
