@@ -174,6 +174,34 @@ def test_observe_all_dtypes_match_reference_stack(g):
         game2.set_board_values(torch.full((len(boards), 16), 3))
 
 
+def test_value_exponent_converters_rows_and_ragged(g):
+    """g2048_values_from_exp / g2048_exp_from_values: the row-per-thread path (whole, aligned rows) and the
+    per-cell path (ragged counts, unaligned pointers) give the same cells; bad values are counted."""
+    import ctypes as C
+    import torch
+    from gym_2048_b200._lib import check, lib
+    L = lib()
+    rng = np.random.default_rng(5)
+    exps = rng.integers(0, 19, 4096 + 64).astype(np.uint8)
+    want = np.where(exps > 0, np.int64(1) << exps.astype(np.int64), 0)
+    d_exp = torch.from_numpy(exps).cuda()
+    for off, cnt in ((0, 4096), (0, 4095), (1, 4093), (4, 4000), (3, 7), (0, 1)):
+        vals = torch.full((4200,), -1, dtype=torch.int64, device="cuda")
+        check(L.g2048_values_from_exp(C.c_void_p(d_exp.data_ptr() + off), C.c_void_p(vals.data_ptr()), cnt, None))
+        assert np.array_equal(vals[:cnt].cpu().numpy(), want[off:off + cnt]) and int(vals[cnt]) == -1
+        back = torch.full((4200,), 255, dtype=torch.uint8, device="cuda")
+        bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+        check(L.g2048_exp_from_values(C.c_void_p(vals.data_ptr()), C.c_void_p(back.data_ptr() + off), cnt,
+                                      C.c_void_p(bad.data_ptr()), None))
+        assert np.array_equal(back[off:off + cnt].cpu().numpy(), exps[off:off + cnt]) and int(back[off + cnt]) == 255
+        assert int(bad) == 0
+    vals = torch.tensor([2, 3, 0, 6, 4, 1, 1 << 31, 1 << 32], dtype=torch.int64, device="cuda")
+    out = torch.empty(8, dtype=torch.uint8, device="cuda")
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(L.g2048_exp_from_values(C.c_void_p(vals.data_ptr()), C.c_void_p(out.data_ptr()), 8, C.c_void_p(bad.data_ptr()), None))
+    assert out.cpu().tolist() == [1, 0, 0, 0, 2, 0, 31, 0] and int(bad) == 4
+
+
 def test_vec_env_sb3_semantics(g):
     n = 512
     venv = g.Game2048VecEnv(n, seed=7, obs_dtype=__import__("torch").uint8)
