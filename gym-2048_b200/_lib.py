@@ -22,7 +22,7 @@ FLAG_AUTO_RESET = 1
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
-    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
+    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
@@ -48,6 +48,17 @@ class StepArgs(C.Structure):
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
+    ]
+
+
+class StepManyArgs(C.Structure):
+    """G2048StepManyArgs (include/g2048.h)."""
+    _fields_ = [
+        ("boards", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
+        ("illegal", C.c_void_p), ("boards_traj", C.c_void_p),
+        ("n", C.c_uint64), ("env_id_base", C.c_uint64), ("seed", C.c_uint64), ("step_index", C.c_uint64),
+        ("n_steps", C.c_uint32), ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -115,6 +126,7 @@ def lib():
     L.g2048_env_step_index.restype = C.c_uint64
     u64, vp, u32 = C.c_uint64, C.c_void_p, C.c_uint32
     L.g2048_step.argtypes = [C.POINTER(StepArgs), vp]
+    L.g2048_step_many.argtypes = [C.POINTER(StepManyArgs), vp]
     L.g2048_reset.argtypes = [vp, vp, u64, u64, u64, u64, vp]
     L.g2048_add_tile.argtypes = [vp, u64, u64, u64, u64, vp]
     L.g2048_move.argtypes = [vp, vp, vp, vp, vp, u64, vp]

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import FLAG_AUTO_RESET, G2048Error, StepArgs, check
+from ._lib import StepManyArgs, FLAG_AUTO_RESET, G2048Error, StepArgs, check
 
 try:                                    # ~0.1 us instead of ~2 us for torch.cuda.current_stream().cuda_stream
     _raw_stream = torch._C._cuda_getCurrentRawStream
@@ -239,6 +239,49 @@ class BatchedGame2048:
         res.boards = self.boards
         res.terminal_boards = terminal_out if terminal_out is not None else self.terminal_boards
         return res
+
+    def step_many(self, actions, rewards=None, dones=None, illegal=None, boards_traj=None):
+        """`K = actions.shape[0]` steps in ONE launch for an open-loop action sequence (`actions`: uint8 [K,n]
+        on the device; pre-generated random actions, a recorded game).  Bit-identical to K calls of step() —
+        same draws, same auto-reset — but the boards stay in registers between the steps (g2048_step_many).
+        Returns (rewards f32 [K,n], dones bool [K,n]); `illegal` (uint8 [K,n]) and `boards_traj`
+        (uint8 [K,n,16], the board handed back after every step) are filled when given.  The optional
+        per-step outputs of step() (legal mask, highest, episode statistics) are not produced: the legal mask
+        is refreshed at the end, episode statistics must not be enabled."""
+        n = self.num_envs
+        if self._step_counter is not None:
+            raise G2048Error("step_many is not available with a device-side step counter")
+        if self.ep_score is not None:
+            raise G2048Error("step_many does not maintain episode statistics: build the env without 'episode'")
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device
+                and actions.is_contiguous() and actions.dim() == 2 and actions.shape[1] == n):
+            raise ValueError("actions must be a contiguous uint8 [K,%d] tensor on %s" % (n, self.device))
+        K = int(actions.shape[0])
+
+        def buf(t, dtype, shape, what):
+            if t is None:
+                return None
+            if not (isinstance(t, torch.Tensor) and t.dtype == dtype and t.device == self.device and t.is_contiguous()
+                    and tuple(t.shape) == shape):
+                raise ValueError("%s must be a contiguous %s %s tensor on %s" % (what, dtype, shape, self.device))
+            return t
+        rewards = buf(rewards, torch.float32, (K, n), "rewards")
+        dones_u8 = buf(dones, torch.uint8, (K, n), "dones")
+        if rewards is None:
+            rewards = torch.empty((K, n), dtype=torch.float32, device=self.device)
+        if dones_u8 is None:
+            dones_u8 = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        illegal = buf(illegal, torch.uint8, (K, n), "illegal")
+        boards_traj = buf(boards_traj, torch.uint8, (K, n, 16), "boards_traj")
+        a = StepManyArgs(self._ptr(self.boards), self._ptr(actions), self._ptr(rewards), self._ptr(dones_u8),
+                         self._ptr(illegal), self._ptr(boards_traj), n, self.env_id_base, self.seed, self.step_index,
+                         K, self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
+        if K:
+            self._launch(self.lib.g2048_step_many, C.byref(a))
+            self.step_index += K
+            if self.legal_mask is not None:
+                self.status(legal_mask=self.legal_mask)
+        return rewards, dones_u8.view(torch.bool)
 
     def sample_actions(self, legal=False, out=None):
         """Uniform-random actions for the NEXT step, drawn on the device from the policy-tag draw stream at that

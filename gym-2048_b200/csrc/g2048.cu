@@ -453,6 +453,80 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------
+// Several steps per launch (g2048_step_many): the same step, applied n_steps times to boards
+// that stay in registers in between.  For open-loop action sequences — pre-generated random
+// actions, replays of recorded games — the board traffic (32 of the 38 bytes of a step) and the
+// per-step launch disappear; per step a thread reads one action byte and writes reward and done.
+// Results are bit-identical to n_steps calls of g2048_step (step k draws with index step_index + k).
+// ------------------------------------------------------------------------------------
+struct ManyParams {
+  uint4* boards;                // [n] in/out
+  const uint8_t* actions;       // [n_steps][row_stride]
+  float* rewards;               // [n_steps][row_stride]
+  uint8_t* dones;               // [n_steps][row_stride]
+  uint8_t* illegal;             // nullable, [n_steps][row_stride]
+  uint4* boards_traj;           // nullable, [n_steps][row_stride]: the board handed back after every step
+  uint32_t n;                   // boards of this launch
+  uint32_t n_steps;
+  uint64_t row_stride;          // boards per step row of the [n_steps][...] arrays (>= n when the call was sliced)
+  uint32_t env_lo;              // low half of board 0's env id (the launch never crosses 2^32 ids)
+  uint32_t idx_lo;              // low half of the first step's index (nor 2^32 indices)
+  uint32_t key;                 // stream_key(seed, step_index, env id, TAG_STEP)
+  StreamKeys keys;              // k[1..9] of that key (k[0] is derived per step)
+  float illegal_move_reward;
+  uint32_t max_tile_exp;
+  uint32_t flags;
+};
+
+template <bool EXTRAS>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_many_kernel(const ManyParams p) {
+  __shared__ alignas(128) Board4 s_lut[1024];
+  __shared__ alignas(8) uint64_t s_lut_bar;
+  __shared__ Sel4 s_sel[8];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_lut_bar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s_lut_bar, (uint32_t)sizeof(PairLut));
+    bulk_load(s_lut, &g_pair_lut, (uint32_t)sizeof(PairLut), &s_lut_bar);
+  }
+#if G2048_PDL
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+  if (threadIdx.x >= 32 && threadIdx.x < 40) {
+    const uint32_t k = threadIdx.x - 32;
+    s_sel[k] = (k < 4) ? kOrientIn[k] : kOrientOut[k - 4];
+  }
+  __syncthreads();
+#if G2048_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+  mbar_wait(&s_lut_bar, 0u);
+  const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
+  const uint32_t n = p.n, stride = gridDim.x * kThreads;
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint4 bd = load_board(p.boards + i);
+    size_t off = i;                                   // element (k, i) of the per-step arrays
+    uint32_t action = p.actions[off];
+    for (uint32_t k = 0; k < p.n_steps; ++k, off += p.row_stride) {
+      const uint32_t act = action & 3u;
+      if (k + 1u < p.n_steps) action = p.actions[off + p.row_stride];       // next step's action, one step ahead
+      uint32_t a, b, c, d;
+      orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
+      const Moved m = move_oriented(a, b, c, d, s_sel[4u + act]);
+      const Words w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.key ^ (p.idx_lo + k), p.keys));
+      const StepOut o = finish_step<true>(s_lut, m, w, p.max_tile_exp, false, auto_reset, bd.x, bd.y, bd.z, bd.w);
+      p.rewards[off] = o.legal ? o.score : p.illegal_move_reward;           // :90 / :95
+      p.dones[off] = o.done ? 1 : 0;
+      if (EXTRAS) {
+        if (p.illegal) p.illegal[off] = o.legal ? 0 : 1;
+        if (p.boards_traj) p.boards_traj[off] = bd;
+      }
+    }
+    p.boards[i] = bd;
+  }
+}
+
 // Game2048Env.reset (:102-111)
 __global__ void __launch_bounds__(kThreads)
 g2048_reset_kernel(uint4* boards, const uint8_t* reset_mask, uint64_t n, uint64_t env_id_base, uint64_t seed,
@@ -794,6 +868,75 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
     if (rc != G2048_OK) return rc;
   }
   return launch_check("g2048_step_kernel");
+}
+
+// One g2048_step_many launch: no 2^32 boundary of env ids or step indices inside.
+static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m, uint64_t k0, uint64_t ks,
+                            cudaStream_t s) {
+  ManyParams p;
+  const uint64_t row0 = k0 * a->n + lo;
+  p.boards = reinterpret_cast<uint4*>(a->boards) + lo;
+  p.actions = a->actions + row0;
+  p.rewards = a->rewards + row0;
+  p.dones = a->dones + row0;
+  p.illegal = a->illegal ? a->illegal + row0 : nullptr;
+  p.boards_traj = a->boards_traj ? reinterpret_cast<uint4*>(a->boards_traj) + row0 : nullptr;
+  p.n = (uint32_t)m;
+  p.n_steps = (uint32_t)ks;
+  p.row_stride = a->n;
+  const uint64_t env0 = a->env_id_base + lo, idx0 = a->step_index + k0;
+  p.env_lo = (uint32_t)env0;
+  p.idx_lo = (uint32_t)idx0;
+  p.key = stream_key(a->seed, idx0, env0, TAG_STEP);
+  make_stream_keys(p.key, 0u, p.keys);
+  p.illegal_move_reward = a->illegal_move_reward;
+  p.max_tile_exp = a->max_tile_exp;
+  p.flags = a->flags;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid_for(m));
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = s;
+#if G2048_PDL
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#endif
+  const bool extras = a->illegal || a->boards_traj;
+  const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<true>, p)
+                                : cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<false>, p);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_many_kernel)");
+  return G2048_OK;
+}
+
+int g2048_step_many(const G2048StepManyArgs* a, void* stream) {
+  if (!a) return fail(G2048_ERR_INVALID, "g2048_step_many: args is NULL");
+  if (a->n == 0 || a->n_steps == 0) return G2048_OK;
+  if (!a->boards || !a->actions || !a->rewards || !a->dones)
+    return fail(G2048_ERR_INVALID, "g2048_step_many: boards, actions, rewards and dones are required");
+  if (!aligned16(a->boards) || !aligned16(a->boards_traj))
+    return fail(G2048_ERR_ALIGN, "g2048_step_many: boards / boards_traj must be 16-byte aligned");
+  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step_many: max_tile_exp %u > 63", a->max_tile_exp);
+  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step_many: n must be < 2^32 - 256 per call");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // The kernel treats the high halves of the env id and of the step index as launch-uniform (they are folded
+  // into the generator's key): a call that crosses a multiple of 2^32 in either is issued in pieces.  Steps
+  // first (a later step reads the boards the earlier one left), boards second.
+  for (uint64_t k0 = 0; k0 < a->n_steps;) {
+    const uint64_t to_idx = 0x100000000ull - ((a->step_index + k0) & 0xFFFFFFFFull);
+    const uint64_t ks = (a->n_steps - k0 < to_idx) ? a->n_steps - k0 : to_idx;
+    for (uint64_t lo = 0; lo < a->n;) {
+      const uint64_t to_env = 0x100000000ull - ((a->env_id_base + lo) & 0xFFFFFFFFull);
+      const uint64_t m = (a->n - lo < to_env) ? a->n - lo : to_env;
+      const int rc = launch_step_many(a, lo, m, k0, ks, s);
+      if (rc != G2048_OK) return rc;
+      lo += m;
+    }
+    k0 += ks;
+  }
+  return launch_check("g2048_step_many_kernel");
 }
 
 int g2048_reset(uint8_t* boards, const uint8_t* reset_mask, uint64_t n, uint64_t env_id_base, uint64_t seed,

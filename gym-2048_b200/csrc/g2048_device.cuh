@@ -152,6 +152,18 @@ G2048_HD void make_stream_keys(uint32_t key, uint32_t idx_lo, StreamKeys& ks) {
   ks.k[0] = key ^ idx_lo;
   for (int r = 1; r < 10; ++r) ks.k[r] = key + (uint32_t)r * PHILOX_W;
 }
+// k0 = key ^ idx_lo given explicitly (a kernel that runs several step indices per launch keeps
+// k[1..9] in constant memory and derives k0 per step).
+G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, uint32_t k0, const StreamKeys& ks) {
+  uint32_t c0 = mulhi32(PHILOX2_M, env_lo) ^ k0, c1 = PHILOX2_M * env_lo;
+#pragma unroll
+  for (int r = 1; r < 10; ++r) {
+    const uint32_t hi = mulhi32(PHILOX2_M, c0), lo = PHILOX2_M * c0;
+    c0 = hi ^ ks.k[r] ^ c1;
+    c1 = lo;
+  }
+  return Pair{c0, c1};
+}
 G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, const StreamKeys& ks) {
   uint32_t c0 = mulhi32(PHILOX2_M, env_lo) ^ ks.k[0], c1 = PHILOX2_M * env_lo;
 #pragma unroll

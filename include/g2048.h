@@ -53,7 +53,8 @@ extern "C" {
 #endif
 
 #define G2048_ABI_VERSION 3 /* 2: G2048StepArgs.boards_out, data-side entry points */
-                            /* 3: draw stream version 2, g2048_philox2x32, g2048_draw_words */
+                            /* 3: draw stream version 2, g2048_philox2x32, g2048_draw_words, */
+                            /*    g2048_step_many                                            */
 
 #define G2048_TAG_STEP   0u
 #define G2048_TAG_RESET  1u
@@ -121,6 +122,35 @@ int g2048_abi_version(void);
 const char* g2048_last_error(void);
 
 int g2048_step(const G2048StepArgs* args, void* stream);
+
+/*
+ * n_steps steps in one launch, for open-loop action sequences (pre-generated random
+ * actions as in `train.py:119`, replays of recorded games): exactly what n_steps calls of
+ * g2048_step with actions + k*n, rewards + k*n, dones + k*n and step_index + k would
+ * leave — same draws, same auto-reset — but the boards stay in registers between
+ * the steps, so a step costs one action byte read and a reward and a done written
+ * instead of 38 bytes, and there is one launch instead of n_steps.  The per-step
+ * arrays are step-major: element (k, i) at k*n + i.
+ */
+typedef struct G2048StepManyArgs {
+  uint8_t*       boards;       /* [n*16]         in/out: before the first / after the last step */
+  const uint8_t* actions;      /* [n_steps*n]    0..3; only the low 2 bits are read             */
+  float*         rewards;      /* [n_steps*n]    out                                            */
+  uint8_t*       dones;        /* [n_steps*n]    out                                            */
+  uint8_t*       illegal;      /* [n_steps*n]    out, nullable                                  */
+  uint8_t*       boards_traj;  /* [n_steps*n*16] out, nullable: the board handed back to the    */
+                               /*                agent after every step (row k = after step k)  */
+  uint64_t       n;
+  uint64_t       env_id_base;
+  uint64_t       seed;
+  uint64_t       step_index;   /* index of the first step; step k uses step_index + k           */
+  uint32_t       n_steps;
+  float          illegal_move_reward;
+  uint32_t       max_tile_exp;
+  uint32_t       flags;        /* G2048_FLAG_*                                                  */
+} G2048StepManyArgs;
+
+int g2048_step_many(const G2048StepManyArgs* args, void* stream);
 
 /*
  * Game2048Env.reset (game2048_env.py:102-111) for every env whose reset_mask

@@ -119,6 +119,13 @@ class OracleBatch:
         return out
 
 
+    def step_many(self, actions):
+        """K consecutive step() calls (the definition of g2048_step_many): per-step outputs stacked [K, ...]."""
+        outs = [self.step(a) for a in np.asarray(actions)]
+        stacked = {k: np.stack([o[k] for o in outs]) for k in ("rewards", "dones", "illegal")}
+        return stacked
+
+
 def add_tile(boards, env_id_base, seed, step_index):
     b = np.ascontiguousarray(boards, dtype=np.uint8).reshape(-1, 16).copy()
     rc = lib().g2048_oracle_add_tile(_p(b), C.c_uint64(len(b)), C.c_uint64(env_id_base), C.c_uint64(seed),

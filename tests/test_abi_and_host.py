@@ -40,6 +40,8 @@ def test_struct_layouts_match_header():
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(G2048StepArgs), offsetof(G2048StepArgs, n),
              offsetof(G2048StepArgs, illegal_move_reward), offsetof(G2048StepArgs, flags),
              sizeof(G2048EnvConfig), sizeof(G2048HostStepOut));
+      printf("%zu %zu %zu %zu\n", sizeof(G2048StepManyArgs), offsetof(G2048StepManyArgs, n),
+             offsetof(G2048StepManyArgs, n_steps), offsetof(G2048StepManyArgs, flags));
       return 0;
     }'''
     d = os.path.join(ROOT, "tests", "host_sim")
@@ -51,6 +53,8 @@ def test_struct_layouts_match_header():
     for S in (g._lib.StepArgs, oracle.StepArgs):
         assert [C.sizeof(S), S.n.offset, S.illegal_move_reward.offset, S.flags.offset] == out[:4]
     assert C.sizeof(g._lib.EnvConfig) == out[4] and C.sizeof(g._lib.HostStepOut) == out[5]
+    M = g._lib.StepManyArgs
+    assert [C.sizeof(M), M.n.offset, M.n_steps.offset, M.flags.offset] == out[6:10]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -207,3 +207,52 @@ def test_lean_kernel_crossing_boundary_and_device_step_counter():
     assert np.array_equal(gm.boards.cpu().numpy(), ref.boards)
     gm.use_device_step_counter(False)
     assert gm.step_index == T
+
+
+@pytest.mark.parametrize("n,K,base,step0,kw", [
+    (1, 5, 0, 0, {}),
+    (33, 1, 7, 3, {}),
+    (1000, 40, 123, 0, dict(illegal_move_reward=-1.0)),
+    (5000, 24, 0, 0, dict(auto_reset=False)),
+    (4096, 64, 0, 11, dict(max_tile_exp=5)),
+    (1000, 6, 2**32 - 500, 0, {}),                    # env ids cross a multiple of 2^32 inside the call
+    (700, 7, 5, 2**32 - 3, {}),                       # step indices cross a multiple of 2^32 inside the call
+    (70001, 16, 2**33 + 1, 2**40, {}),                # several boards per thread, ragged tail
+])
+def test_step_many_is_k_steps(n, K, base, step0, kw):
+    """g2048_step_many == K calls of step(): against the oracle stepped K times (rewards, dones, illegal, the
+    board after every step) and against the product's own single-step kernel."""
+    import torch
+    import gym_2048_b200 as g
+    from oracle import oracle
+    seed = 1234567
+    rng = np.random.default_rng(n + K)
+    actions = rng.integers(0, 4, (K, n)).astype(np.uint8)
+    max_tile = None if not kw.get("max_tile_exp") else 2 ** kw["max_tile_exp"]
+    mk = lambda outputs: g.BatchedGame2048(n, seed=seed, env_id_base=base, outputs=outputs, max_tile=max_tile,
+                                           illegal_move_reward=kw.get("illegal_move_reward", 0.0),
+                                           auto_reset=kw.get("auto_reset", True))
+    ref = oracle.OracleBatch(n, seed=seed, env_id_base=base, **kw)
+    ref.reset()
+    ref.step_index = step0
+    many, single, lean = mk(("illegal",)), mk(("illegal",)), mk(())
+    for game in (many, single, lean):
+        game.reset()
+        game.step_index = step0
+        assert np.array_equal(game.boards.cpu().numpy(), ref.boards)
+    d_act = torch.from_numpy(actions).cuda()
+    illegal = torch.empty((K, n), dtype=torch.uint8, device="cuda")
+    traj = torch.empty((K, n, 16), dtype=torch.uint8, device="cuda")
+    rewards, dones = many.step_many(d_act, illegal=illegal, boards_traj=traj)
+    rewards_lean, dones_lean = lean.step_many(d_act)
+    assert many.step_index == step0 + K
+    for k in range(K):
+        o = ref.step(actions[k])
+        r = single.step(d_act[k])
+        assert np.array_equal(rewards[k].cpu().numpy(), o["rewards"]), k
+        assert np.array_equal(dones[k].cpu().numpy().astype(np.uint8), o["dones"]), k
+        assert np.array_equal(illegal[k].cpu().numpy(), o["illegal"]), k
+        assert np.array_equal(traj[k].cpu().numpy(), ref.boards), k
+        assert torch.equal(r.rewards, rewards[k]) and torch.equal(r.dones, dones[k]) and torch.equal(r.boards, traj[k])
+    assert torch.equal(many.boards, traj[K - 1]) and torch.equal(lean.boards, many.boards)
+    assert torch.equal(rewards_lean, rewards) and torch.equal(dones_lean, dones)
