@@ -36,7 +36,7 @@ def main():
     ki = hdr.index("Kernel Name")
     md = ["# %s — ncu capture of the step kernel (B200, sm_100a)" % tag, "",
           "Source: `gpurun_out/step_full.ncu-rep` (`ncu --set full --clock-control none --import-source on "
-          "-k regex:g2048_step_kernel -s 60 -c 3 python bench.py --steps 100 --warmup 20`), summarised by "
+          "-k regex:g2048_step_kernel -s 60 -c 3 python bench.py --steps 100 --warmup 20 --e2e-steps 3 --fused-steps 0`), summarised by "
           "`scripts/summarize_ncu.py`.  Kernel: `%s`, %d captured launches of 1,048,576 boards each.  ncu "
           "serialises launches and flushes caches between replays, so durations are cold-cache and exclude the "
           "programmatic-dependent-launch overlap of the real run; compare shares, not absolutes." %
@@ -86,7 +86,7 @@ def main():
             agg[r[kn]].append(float(r[mv].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(PROF, "%s_launches_summary.md" % tag), "w") as f:
-        f.write("# " + tag + " — ncu launch list of `python bench.py --steps 100 --warmup 20` (gpu__time_duration.sum, ns)\n\n"
+        f.write("# " + tag + " — ncu launch list of `python bench.py --steps 100 --warmup 20 --e2e-steps 3 --fused-steps 0` (gpu__time_duration.sum, ns)\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200`; per-launch times are "
                 "cold-cache and serialised.  The timed region of bench.py launches only `g2048_step_kernel<0, 0>` (lean outputs, host-side step index); "
                 "`<1, 0>` and the reset kernel belong to the e2e leg and set-up.\n\n"
