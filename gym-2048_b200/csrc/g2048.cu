@@ -78,6 +78,25 @@ unsigned grid_for(uint64_t n) {
   return (unsigned)(need < cap ? need : cap);
 }
 
+// Launch shape of the step kernels.  A batch that fills the machine runs as one persistent wave of
+// kCtasPerSm kThreads-wide CTAs per SM.  A smaller one is cut into 128-thread CTAs, and because the block
+// scheduler packs CTAs onto an SM up to its residency limit before it moves on to the next SM (65,536 boards as
+// 128 CTAs of 512 threads land on 64 SMs, two each, and leave 84 idle), the residency limit itself is set to
+// the even share, ceil(CTAs / SMs), by padding every CTA with dynamic shared memory it never touches.
+struct LaunchShape { unsigned grid, block; size_t pad_smem; };
+static LaunchShape shape_for(uint64_t n, size_t static_smem) {
+  const uint64_t sms = (uint64_t)sm_count();
+  const uint64_t full_ctas = (n + kThreads - 1) / kThreads;
+  if (full_ctas >= sms * kCtasPerSm) return LaunchShape{grid_for(n), (unsigned)kThreads, 0};
+  const unsigned block = 128u;
+  const uint64_t ctas = (n + block - 1) / block;
+  const uint64_t per_sm = (ctas + sms - 1) / sms;                          // 1 .. 8
+  const size_t budget = (size_t)220 * 1024 / per_sm;                       // of the 227 KB an SM can carve out
+  const size_t fixed = static_smem + 1024 + 256;                           // + the per-CTA reserve
+  return LaunchShape{(unsigned)ctas, block, budget > fixed ? (budget - fixed) / 1024 * 1024 : 0};
+}
+constexpr int kMaxPadSmem = 208 * 1024;
+
 // ------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------
@@ -292,8 +311,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
   const uint32_t n = p.n;
 #if !G2048_TMA
-  const uint32_t stride = gridDim.x * kThreads;
-  uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t stride = gridDim.x * blockDim.x;               // the CTA width is chosen at launch (shape_for)
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 #endif
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -503,8 +522,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_many_kernel(c
 #endif
   mbar_wait(&s_lut_bar, 0u);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
-  const uint32_t n = p.n, stride = gridDim.x * kThreads;
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+  const uint32_t n = p.n, stride = gridDim.x * blockDim.x;       // the CTA size is chosen at launch (see launch_step_many)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint4 bd = load_board(p.boards + i);
     size_t off = i;                                   // element (k, i) of the per-step arrays
     uint32_t action = p.actions[off];
@@ -803,12 +822,34 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
                       a->ep_len || a->final_score || a->final_len || a->forced_draws;
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
-#if G2048_PERSISTENT
+#if G2048_TMA || !G2048_PAIR_LUT
   cfg.gridDim = dim3(grid_for(a->n));
+  cfg.blockDim = dim3(kThreads);
+#elif G2048_PERSISTENT
+  const LaunchShape shape = shape_for(a->n, sizeof(PairLut) + 256);
+  cfg.gridDim = dim3(shape.grid);
+  cfg.blockDim = dim3(shape.block);
+  cfg.dynamicSmemBytes = shape.pad_smem;
+  {
+    static thread_local int prepared_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != prepared_dev) {                       // once per device and thread: allow the padding, prefer shared memory
+      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      prepared_dev = dev;
+    }
+  }
 #else
   cfg.gridDim = dim3((unsigned)((a->n + kThreads - 1) / kThreads));
-#endif
   cfg.blockDim = dim3(kThreads);
+#endif
   cfg.stream = s;
 #if G2048_PDL
   cudaLaunchAttribute attr[1];
@@ -892,10 +933,12 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = a->flags;
+  const LaunchShape shape = shape_for(m, sizeof(PairLut) + 256);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(grid_for(m));
-  cfg.blockDim = dim3(kThreads);
+  cfg.gridDim = dim3(shape.grid);
+  cfg.blockDim = dim3(shape.block);
+  cfg.dynamicSmemBytes = shape.pad_smem;
   cfg.stream = s;
 #if G2048_PDL
   cudaLaunchAttribute attr[1];
@@ -904,6 +947,19 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 #endif
+  {
+    // once per device and thread: allow the padding of shape_for, prefer shared memory over L1
+    static thread_local int prepared_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != prepared_dev) {
+      cudaFuncSetAttribute(g2048_step_many_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(g2048_step_many_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      cudaFuncSetAttribute(g2048_step_many_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      cudaFuncSetAttribute(g2048_step_many_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      prepared_dev = dev;
+    }
+  }
   const bool extras = a->illegal || a->boards_traj;
   const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<true>, p)
                                 : cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<false>, p);
