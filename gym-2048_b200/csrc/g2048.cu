@@ -77,6 +77,15 @@ unsigned grid_for(uint64_t n) {
   const uint64_t cap = (uint64_t)sm_count() * kCtasPerSm;
   return (unsigned)(need < cap ? need : cap);
 }
+// The streaming kernels (observation encoder, move, status, symmetries, ...) use few registers, so four of
+// their CTAs fit an SM — and the block scheduler fills an SM to its residency limit before it moves on: a
+// grid of two CTAs per SM would run on half the SMs.  Their persistent grid is therefore four CTAs per SM
+// (observation encoder 84 -> 57 us per 1 Mi boards, profiles/r01_kernels.md).
+unsigned grid_for_streaming(uint64_t n) {
+  const uint64_t need = (n + kThreads - 1) / kThreads;
+  const uint64_t cap = (uint64_t)sm_count() * 4u;
+  return (unsigned)(need < cap ? need : cap);
+}
 
 // Launch shape of the step kernels.  A batch that fills the machine runs as one persistent wave of
 // kCtasPerSm kThreads-wide CTAs per SM.  A smaller one is cut into 128-thread CTAs, and because the block
@@ -1010,7 +1019,7 @@ int g2048_add_tile(uint8_t* boards, uint64_t n, uint64_t env_id_base, uint64_t s
   if (n == 0) return G2048_OK;
   if (!boards) return fail(G2048_ERR_INVALID, "g2048_add_tile: boards is NULL");
   if (!aligned16(boards)) return fail(G2048_ERR_ALIGN, "g2048_add_tile: boards must be 16-byte aligned");
-  g2048_add_tile_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  g2048_add_tile_kernel<<<grid_for_streaming(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<uint4*>(boards), n, env_id_base, seed, step_index);
   return launch_check("g2048_add_tile_kernel");
 }
@@ -1021,7 +1030,7 @@ int g2048_move(const uint8_t* boards_in, uint8_t* boards_out, const uint8_t* dir
   if (!boards_in || !directions) return fail(G2048_ERR_INVALID, "g2048_move: boards_in and directions are required");
   if (!aligned16(boards_in) || !aligned16(boards_out))
     return fail(G2048_ERR_ALIGN, "g2048_move: boards must be 16-byte aligned");
-  g2048_move_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  g2048_move_kernel<<<grid_for_streaming(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(boards_in), reinterpret_cast<uint4*>(boards_out), directions, scores,
       changed, n);
   return launch_check("g2048_move_kernel");
@@ -1032,7 +1041,7 @@ int g2048_status(const uint8_t* boards, uint8_t* legal_mask_out, uint8_t* highes
   if (n == 0) return G2048_OK;
   if (!boards) return fail(G2048_ERR_INVALID, "g2048_status: boards is NULL");
   if (!aligned16(boards)) return fail(G2048_ERR_ALIGN, "g2048_status: boards must be 16-byte aligned");
-  g2048_status_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  g2048_status_kernel<<<grid_for_streaming(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(boards), legal_mask_out, highest_out, n_empty, is_end, max_tile_exp, n);
   return launch_check("g2048_status_kernel");
 }
@@ -1046,10 +1055,10 @@ int g2048_encode_obs(const uint8_t* boards, void* obs, int dtype, uint64_t n, vo
   const uint32_t* b = reinterpret_cast<const uint32_t*>(boards);
   uint4* o = static_cast<uint4*>(obs);
   switch (dtype) {
-    case G2048_OBS_U8:   g2048_obs_kernel<uint8_t><<<grid_for(n << 4), kThreads, 0, s>>>(b, o, n << 4); break;
-    case G2048_OBS_BF16: g2048_obs_kernel<bf16x4><<<grid_for(n << 5), kThreads, 0, s>>>(b, o, n << 5); break;
-    case G2048_OBS_F32:  g2048_obs_kernel<float><<<grid_for(n << 6), kThreads, 0, s>>>(b, o, n << 6); break;
-    case G2048_OBS_I64:  g2048_obs_kernel<int64_t><<<grid_for(n << 7), kThreads, 0, s>>>(b, o, n << 7); break;
+    case G2048_OBS_U8:   g2048_obs_kernel<uint8_t><<<grid_for_streaming(n << 4), kThreads, 0, s>>>(b, o, n << 4); break;
+    case G2048_OBS_BF16: g2048_obs_kernel<bf16x4><<<grid_for_streaming(n << 5), kThreads, 0, s>>>(b, o, n << 5); break;
+    case G2048_OBS_F32:  g2048_obs_kernel<float><<<grid_for_streaming(n << 6), kThreads, 0, s>>>(b, o, n << 6); break;
+    case G2048_OBS_I64:  g2048_obs_kernel<int64_t><<<grid_for_streaming(n << 7), kThreads, 0, s>>>(b, o, n << 7); break;
     default: return fail(G2048_ERR_INVALID, "g2048_encode_obs: unknown dtype %d", dtype);
   }
   return launch_check("g2048_obs_kernel");
@@ -1073,7 +1082,7 @@ int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cel
   if (!boards || !values) return fail(G2048_ERR_INVALID, "g2048_exp_from_values: NULL pointer");
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   if ((n_cells & 3u) == 0 && (reinterpret_cast<uintptr_t>(boards) & 3u) == 0 && aligned16(values))   // whole rows
-    g2048_exp_from_values4_kernel<<<grid_for(n_cells / 4), kThreads, 0, s>>>(
+    g2048_exp_from_values4_kernel<<<grid_for_streaming(n_cells / 4), kThreads, 0, s>>>(
         reinterpret_cast<const longlong2*>(values), reinterpret_cast<uint32_t*>(boards), n_cells / 4, bad_count);
   else
     g2048_exp_from_values_kernel<<<grid_for(n_cells), kThreads, 0, s>>>(values, boards, n_cells, bad_count);

@@ -152,7 +152,7 @@ int g2048_symmetry(const uint8_t* boards_in, uint8_t* boards_out, const uint8_t*
     return fail(G2048_ERR_INVALID, "g2048_symmetry: next_in/next_out and actions_in/actions_out come in pairs");
   if (!aligned16(boards_in) || !aligned16(boards_out) || !aligned16(next_in) || !aligned16(next_out))
     return fail(G2048_ERR_ALIGN, "g2048_symmetry: boards must be 16-byte aligned");
-  g2048_symmetry_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  g2048_symmetry_kernel<<<grid_for_streaming(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(boards_in), reinterpret_cast<uint4*>(boards_out),
       reinterpret_cast<const uint4*>(next_in), reinterpret_cast<uint4*>(next_out), actions_in, actions_out, n,
       hflip ? 1 : 0, ((k % 4) + 4) % 4);
@@ -168,7 +168,7 @@ int g2048_augment(const uint8_t* boards, const uint8_t* next_boards, const uint8
     return fail(G2048_ERR_INVALID, "g2048_augment: NULL pointer");
   if (!aligned16(boards) || !aligned16(next_boards) || !aligned16(boards_out) || !aligned16(next_boards_out))
     return fail(G2048_ERR_ALIGN, "g2048_augment: boards must be 16-byte aligned");
-  g2048_augment_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  g2048_augment_kernel<<<grid_for_streaming(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(boards), reinterpret_cast<const uint4*>(next_boards), actions, rewards, dones, n,
       reinterpret_cast<uint4*>(boards_out), reinterpret_cast<uint4*>(next_boards_out), actions_out, rewards_out,
       dones_out);

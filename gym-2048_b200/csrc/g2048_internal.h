@@ -18,6 +18,8 @@ int cuda_fail(cudaError_t e, const char* what);
 int launch_check(const char* name);
 // grid size for a grid-stride kernel over n items: one persistent wave over the SMs at most
 unsigned grid_for(uint64_t n);
+// the same with four CTAs per SM, for the low-register streaming kernels (see g2048.cu)
+unsigned grid_for_streaming(uint64_t n);
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 #define G2048_CUDA(call)                                          \
