@@ -439,16 +439,17 @@ G2048_DEV bool full_board_is_dead(uint32_t r0, uint32_t r1, uint32_t r2, uint32_
 // A line moves toward its head iff some cell is empty with a tile right behind it, or
 // two adjacent tiles are equal.
 G2048_DEV uint32_t legal_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-  const uint32_t n0 = r0 + L7, n1 = r1 + L7, n2 = r2 + L7, n3 = r3 + L7;   // bit7: non-empty
+  // (the adds go to the FMA pipe, addf: the ALU pipe is the step kernel's critical one)
+  const uint32_t n0 = addf(r0, L7), n1 = addf(r1, L7), n2 = addf(r2, L7), n3 = addf(r3, L7);   // bit7: non-empty
   // vertical pairs (upper u, lower l)
-  const uint32_t eqv = (~((r0 ^ r1) + L7) & n0) | (~((r1 ^ r2) + L7) & n1) | (~((r2 ^ r3) + L7) & n2);
+  const uint32_t eqv = (~addf(r0 ^ r1, L7) & n0) | (~addf(r1 ^ r2, L7) & n1) | (~addf(r2 ^ r3, L7) & n2);
   const uint32_t up = (~n0 & n1) | (~n1 & n2) | (~n2 & n3) | eqv;     // hole above a tile
   const uint32_t dn = (n0 & ~n1) | (n1 & ~n2) | (n2 & ~n3) | eqv;     // hole below a tile
   // horizontal pairs: byte j of s_i is cell (i, j+1); only byte lanes 0..2 are pairs
   const uint32_t s0 = r0 >> 8, s1 = r1 >> 8, s2 = r2 >> 8, s3 = r3 >> 8;
-  const uint32_t m0 = s0 + L7, m1 = s1 + L7, m2 = s2 + L7, m3 = s3 + L7;
-  const uint32_t eqh = (~((r0 ^ s0) + L7) & n0) | (~((r1 ^ s1) + L7) & n1) |
-                       (~((r2 ^ s2) + L7) & n2) | (~((r3 ^ s3) + L7) & n3);
+  const uint32_t m0 = addf(s0, L7), m1 = addf(s1, L7), m2 = addf(s2, L7), m3 = addf(s3, L7);
+  const uint32_t eqh = (~addf(r0 ^ s0, L7) & n0) | (~addf(r1 ^ s1, L7) & n1) |
+                       (~addf(r2 ^ s2, L7) & n2) | (~addf(r3 ^ s3, L7) & n3);
   const uint32_t lf = (~n0 & m0) | (~n1 & m1) | (~n2 & m2) | (~n3 & m3) | eqh;   // hole left of a tile
   const uint32_t rt = (n0 & ~m0) | (n1 & ~m1) | (n2 & ~m2) | (n3 & ~m3) | eqh;   // hole right of a tile
   constexpr uint32_t HP = 0x00808080u;                                           // pair lanes only
