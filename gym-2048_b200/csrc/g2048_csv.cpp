@@ -60,9 +60,7 @@ std::string header(bool with_returns) {
 int exp_of(long long v) {
   if (v == 0) return 0;
   if (v < 2 || v > (1ll << 31) || (v & (v - 1))) return -1;
-  int e = 0;
-  while ((1ll << e) < v) ++e;
-  return e;
+  return __builtin_ctzll((unsigned long long)v);
 }
 
 struct File {
@@ -74,6 +72,16 @@ struct File {
 bool read_all(const char* path, std::vector<char>& out) {
   File fp(std::fopen(path, "rb"));
   if (!fp.f) return false;
+  if (std::fseek(fp.f, 0, SEEK_END) == 0) {                       // regular file: one read of the known size
+    const long size = std::ftell(fp.f);
+    if (size >= 0 && std::fseek(fp.f, 0, SEEK_SET) == 0) {
+      out.resize((size_t)size + 1);
+      const size_t k = std::fread(out.data(), 1, (size_t)size, fp.f);
+      out.resize(k + 1);
+      out[k] = '\0';
+      return true;
+    }
+  }
   char buf[1 << 16];
   size_t k;
   while ((k = std::fread(buf, 1, sizeof buf, fp.f)) > 0) out.insert(out.end(), buf, buf + k);
@@ -99,6 +107,34 @@ void data_lines(std::vector<char>& txt, std::vector<char*>& lines, int* header_c
     if (!e) break;
     p = e + 1;
   }
+}
+
+// Integer column: optional sign, decimal digits (what "%d" / "%i" print).  *end == p on failure.
+inline long long parse_int(char* p, char** end) {
+  char* q = p;
+  bool neg = false;
+  if (*q == '-' || *q == '+') neg = *q++ == '-';
+  if (*q < '0' || *q > '9') { *end = p; return 0; }
+  unsigned long long v = 0;
+  while (*q >= '0' && *q <= '9') v = v * 10u + (unsigned)(*q++ - '0');
+  *end = q;
+  return neg ? -(long long)v : (long long)v;
+}
+// Float column.  "%f" output of an integral value below 2^53 — digits '.' zeros, every reward the step
+// produces — is converted exactly without strtod; anything else goes through strtod.
+inline double parse_float(char* p, char** end) {
+  char* q = p;
+  bool neg = false;
+  if (*q == '-') { neg = true; ++q; }
+  unsigned long long v = 0;
+  int digits = 0;
+  while (*q >= '0' && *q <= '9' && digits < 15) { v = v * 10u + (unsigned)(*q++ - '0'); ++digits; }
+  if (digits > 0 && *q == '.') {
+    char* z = q + 1;
+    while (*z == '0') ++z;
+    if (*z == ',' || *z == '\0' || *z == '\r' || *z == '\n') { *end = z; return neg ? -(double)v : (double)v; }
+  }
+  return std::strtod(p, end);
 }
 
 }  // namespace
@@ -175,8 +211,8 @@ int g2048_csv_import(const char* path, uint8_t* boards, uint8_t* actions, double
       const bool is_float = (c == 17 || c == 35);
       double fv = 0.0;
       long long iv = 0;
-      if (is_float) fv = std::strtod(p, &e);
-      else iv = std::strtoll(p, &e, 10);
+      if (is_float) fv = parse_float(p, &e);
+      else iv = parse_int(p, &e);
       if (e == p || (c + 1 < cols ? *e != ',' : (*e != '\0' && *e != '\r')))
         return fail(G2048_ERR_INVALID, "g2048_csv_import: %s row %llu column %d: cannot parse", path,
                     (unsigned long long)(i + 1), c + 1);
