@@ -148,6 +148,60 @@ def c5(args):
     return out
 
 
+def ev(args):
+    """train.py's evaluate_model, batched: 16,384 episodes to the end (or the 2001-move cap), greedy on a fixed
+    preference order with illegal moves masked (a corner strategy; ~180 moves per episode), and on the random-init
+    ResNet policy in bf16."""
+    n = 16384 if not args.quick else 1024
+    pref = torch.tensor([[4.0, 1.0, 2.0, 3.0]], device=DEV)
+    out = {"config": "eval", "workload": "%d episodes, evaluate_model semantics (illegal reward -1, 2001-move cap)" % n}
+    net = g.ResNetActorCritic().to(DEV).eval().to(torch.bfloat16).to(memory_format=torch.channels_last)
+
+    def resnet(obs):
+        return net(obs.to(memory_format=torch.channels_last))[0]
+    for name, model, dt in (("fixed_preference", lambda obs: pref.expand(obs.shape[0], 4), torch.uint8),
+                            ("resnet_bf16", resnet, torch.bfloat16)):
+        g.evaluate_model(model, 256, mask_illegal=True, obs_dtype=dt, device=DEV)          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = g.evaluate_model(model, n, mask_illegal=True, obs_dtype=dt, device=DEV)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        moves = sum(e["moves"] for e in res["Episodes"])
+        out[name] = {"wall_s": wall, "episodes_per_s": n / wall, "env_steps_per_s": moves / wall,
+                     "mean_moves": moves / n, "average_score": res["Average score"], "highest_tile": res["Highest tile"]}
+    return out
+
+
+def rec(args):
+    """gather_training_data.py's recording loop, batched: 4,096 envs x 256 steps of random-legal play recorded out of
+    place, then transitions() (game order, illegal moves dropped), augment() (8 symmetries) and the discounted
+    return, all on the device."""
+    n, T = 4096, 256
+    game = g.BatchedGame2048(n, seed=0, device=DEV, illegal_move_reward=-1.0, outputs=("illegal", "legal_mask"))
+    game.reset()
+    recorder = g.TransitionRecorder(game, horizon=T)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(T):
+        recorder.step(game.sample_actions(legal=True))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    data = recorder.transitions()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    rows = data.size()
+    data.augment()
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    data.get_discounted_return(0.99)
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    return {"config": "recorder", "workload": "4,096 envs x 256 random-legal steps recorded, then transitions / augment / returns",
+            "record_s": t1 - t0, "record_env_steps_per_s": n * T / (t1 - t0), "rows": rows,
+            "transitions_s": t2 - t1, "augment_s": t3 - t2, "augmented_rows": data.size(), "returns_s": t4 - t3}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["c2", "c4", "c5"])
@@ -156,7 +210,7 @@ def main():
     args = ap.parse_args()
     torch.cuda.set_device(0)
     for c in args.configs:
-        res = {"c2": c2, "c4": c4, "c5": c5}[c](args)
+        res = {"c2": c2, "c4": c4, "c5": c5, "eval": ev, "rec": rec}[c](args)
         res["gpu"] = torch.cuda.get_device_name(0)
         print(json.dumps(res), flush=True)
 
