@@ -60,6 +60,16 @@ int cuda_fail(cudaError_t e, const char* what) {
 #define G2048_STAGES 4
 #endif
 constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
+// The step kernels' own persistent shape.  One 1024-thread CTA per SM measured 1 % faster than two of 512
+// (12.23 vs 12.37 us per 1 Mi boards): with two CTAs the hardware scheduler favours the older one and the SM
+// spends the last third of the launch on the younger one's 16 warps alone (scripts/micro/timeline.cu).
+#ifndef G2048_STEP_THREADS
+#define G2048_STEP_THREADS 1024
+#endif
+#ifndef G2048_STEP_CTAS_PER_SM
+#define G2048_STEP_CTAS_PER_SM 1
+#endif
+constexpr int kStepThreads = G2048_STEP_THREADS, kStepCtasPerSm = G2048_STEP_CTAS_PER_SM;
 static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");
 
 static int sm_count() {
@@ -88,15 +98,15 @@ unsigned grid_for_streaming(uint64_t n) {
 }
 
 // Launch shape of the step kernels.  A batch that fills the machine runs as one persistent wave of
-// kCtasPerSm kThreads-wide CTAs per SM.  A smaller one is cut into 128-thread CTAs, and because the block
+// kStepCtasPerSm kStepThreads-wide CTAs per SM.  A smaller one is cut into 128-thread CTAs, and because the block
 // scheduler packs CTAs onto an SM up to its residency limit before it moves on to the next SM (65,536 boards as
 // 128 CTAs of 512 threads land on 64 SMs, two each, and leave 84 idle), the residency limit itself is set to
 // the even share, ceil(CTAs / SMs), by padding every CTA with dynamic shared memory it never touches.
 struct LaunchShape { unsigned grid, block; size_t pad_smem; };
 static LaunchShape shape_for(uint64_t n, size_t static_smem) {
   const uint64_t sms = (uint64_t)sm_count();
-  const uint64_t full_ctas = (n + kThreads - 1) / kThreads;
-  if (full_ctas >= sms * kCtasPerSm) return LaunchShape{grid_for(n), (unsigned)kThreads, 0};
+  const uint64_t full_ctas = (n + kStepThreads - 1) / kStepThreads;
+  if (full_ctas >= sms * kStepCtasPerSm) return LaunchShape{(unsigned)(sms * kStepCtasPerSm), (unsigned)kStepThreads, 0};
   const unsigned block = 128u;
   const uint64_t ctas = (n + block - 1) / block;
   const uint64_t per_sm = (ctas + sms - 1) / sms;                          // 1 .. 8
@@ -277,7 +287,7 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 }
 
 template <bool EXTRAS, bool COUNTER>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kernel(const StepParams p) {
 #if G2048_PAIR_LUT && !G2048_TMA
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
@@ -292,12 +302,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
 #endif
   __shared__ Sel4 s_sel[8];     // [action] = kOrientIn, [4 + action] = kOrientOut
 #if G2048_TMA
-  __shared__ alignas(128) uint4 s_boards[kStages][kThreads];
-  __shared__ alignas(16) uint8_t s_actions[kStages][kThreads];
+  __shared__ alignas(128) uint4 s_boards[kStages][kStepThreads];
+  __shared__ alignas(16) uint8_t s_actions[kStages][kStepThreads];
   __shared__ alignas(8) uint64_t s_full[kStages], s_empty[kStages];
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < kStages; ++k) { mbar_init(&s_full[k], 1u); mbar_init(&s_empty[k], kThreads / 32u); }
+    for (int k = 0; k < kStages; ++k) { mbar_init(&s_full[k], 1u); mbar_init(&s_empty[k], kStepThreads / 32u); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #endif
@@ -345,22 +355,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   // a whole iteration before it is used.  (Unrolling by two was measured slower: the doubled
   // body no longer fits the L0 instruction cache; so were two boards per thread.)
 #if G2048_TMA
-  // Staged loop.  The CTA walks tiles of kThreads consecutive boards (tile t = blockIdx.x + k * gridDim.x).  One
+  // Staged loop.  The CTA walks tiles of kStepThreads consecutive boards (tile t = blockIdx.x + k * gridDim.x).  One
   // elected thread keeps kStages - 1 tiles in flight: per tile two bulk async copies (TMA, cp.async.bulk) bring
   // the 16-byte boards and the action bytes into a shared-memory ring and complete on the stage's `full`
   // mbarrier; every thread waits on that barrier, takes its board and action with one LDS.128 and one LDS.U8,
   // and each warp then arrives on the stage's `empty` barrier, which the producer waits on before it refills
   // the stage.  Loads are thus decoupled from the registers and run several iterations ahead of the compute.
   const uint32_t tid = threadIdx.x;
-  const uint32_t n_tiles = (n + kThreads - 1u) / kThreads;
+  const uint32_t n_tiles = (n + kStepThreads - 1u) / kStepThreads;
   const bool actions_by_tma = (reinterpret_cast<uintptr_t>(p.actions) & 15u) == 0u;
-  auto tile_count = [&](uint32_t t) { const uint32_t left = n - t * kThreads; return left < (uint32_t)kThreads ? left : (uint32_t)kThreads; };
+  auto tile_count = [&](uint32_t t) { const uint32_t left = n - t * kStepThreads; return left < (uint32_t)kStepThreads ? left : (uint32_t)kStepThreads; };
   auto produce = [&](uint32_t t, uint32_t stage) {      // one thread: arm the barrier, start the copies of tile t
     const uint32_t cnt = tile_count(t);
     const bool act_tma = actions_by_tma && (cnt & 15u) == 0u;
     mbar_expect_tx(&s_full[stage], cnt * 16u + (act_tma ? cnt : 0u));
-    bulk_load(&s_boards[stage][0], p.boards + (size_t)t * kThreads, cnt * 16u, &s_full[stage]);
-    if (act_tma) bulk_load(&s_actions[stage][0], p.actions + (size_t)t * kThreads, cnt, &s_full[stage]);
+    bulk_load(&s_boards[stage][0], p.boards + (size_t)t * kStepThreads, cnt * 16u, &s_full[stage]);
+    if (act_tma) bulk_load(&s_actions[stage][0], p.actions + (size_t)t * kStepThreads, cnt, &s_full[stage]);
   };
   if (tid == 0) {
 #pragma unroll
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_kernel(const 
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     const uint32_t cnt = tile_count(t);
     const bool act_tma = actions_by_tma && (cnt & 15u) == 0u;
-    const uint32_t i = t * kThreads + tid;
+    const uint32_t i = t * kStepThreads + tid;
     const bool valid = tid < cnt;
     if (tid == 0) {
       // Refill the stage the CTA consumed in the previous iteration (all warps have normally left it).
@@ -508,7 +518,7 @@ struct ManyParams {
 };
 
 template <bool EXTRAS>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) g2048_step_many_kernel(const ManyParams p) {
+__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_kernel(const ManyParams p) {
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
   __shared__ Sel4 s_sel[8];
@@ -832,8 +842,11 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
 #if G2048_TMA || !G2048_PAIR_LUT
-  cfg.gridDim = dim3(grid_for(a->n));
-  cfg.blockDim = dim3(kThreads);
+  {
+    const uint64_t need = (a->n + kStepThreads - 1) / kStepThreads, cap = (uint64_t)sm_count() * kStepCtasPerSm;
+    cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
+  }
+  cfg.blockDim = dim3(kStepThreads);
 #elif G2048_PERSISTENT
   const LaunchShape shape = shape_for(a->n, sizeof(PairLut) + 256);
   cfg.gridDim = dim3(shape.grid);
@@ -856,8 +869,8 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
     }
   }
 #else
-  cfg.gridDim = dim3((unsigned)((a->n + kThreads - 1) / kThreads));
-  cfg.blockDim = dim3(kThreads);
+  cfg.gridDim = dim3((unsigned)((a->n + kStepThreads - 1) / kStepThreads));
+  cfg.blockDim = dim3(kStepThreads);
 #endif
   cfg.stream = s;
 #if G2048_PDL
