@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 ABI_VERSION = 3
 FLAG_AUTO_RESET = 1
+FLAG_POLICY_UNIFORM, FLAG_POLICY_LEGAL = 2, 4
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
@@ -58,7 +59,7 @@ class StepManyArgs(C.Structure):
         ("illegal", C.c_void_p), ("boards_traj", C.c_void_p),
         ("n", C.c_uint64), ("env_id_base", C.c_uint64), ("seed", C.c_uint64), ("step_index", C.c_uint64),
         ("n_steps", C.c_uint32), ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("actions_out", C.c_void_p), ("legal_mask", C.c_void_p),
     ]
 
 

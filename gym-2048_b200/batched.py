@@ -240,23 +240,41 @@ class BatchedGame2048:
         res.terminal_boards = terminal_out if terminal_out is not None else self.terminal_boards
         return res
 
-    def step_many(self, actions, rewards=None, dones=None, illegal=None, boards_traj=None):
-        """`K = actions.shape[0]` steps in ONE launch for an open-loop action sequence (`actions`: uint8 [K,n]
-        on the device; pre-generated random actions, a recorded game).  Bit-identical to K calls of step() —
-        same draws, same auto-reset — but the boards stay in registers between the steps (g2048_step_many).
-        Returns (rewards f32 [K,n], dones bool [K,n]); `illegal` (uint8 [K,n]) and `boards_traj`
-        (uint8 [K,n,16], the board handed back after every step) are filled when given.  The optional
-        per-step outputs of step() (legal mask, highest, episode statistics) are not produced: the legal mask
-        is refreshed at the end, episode statistics must not be enabled."""
+    def step_many(self, actions=None, rewards=None, dones=None, illegal=None, boards_traj=None, policy=None,
+                  n_steps=None, actions_out=None, legal_mask_out=None):
+        """K steps in ONE launch (g2048_step_many), bit-identical to K calls of step() — same draws, same
+        auto-reset — with the boards staying in registers between the steps.
+
+        Either `actions` (uint8 [K,n] on the device: an open-loop sequence — pre-generated random actions, a
+        recorded game), or `policy` = "uniform" / "legal" with `n_steps` = K: the kernel then plays
+        sample_actions()'s policy itself (the action of step k is what sample_actions(legal=...) would return
+        before that step) and writes the actions it chose to `actions_out` (uint8 [K,n]) when given.
+        Returns (rewards f32 [K,n], dones bool [K,n]); `illegal` (uint8 [K,n]), `boards_traj` (uint8 [K,n,16],
+        the board handed back after every step) and `legal_mask_out` (uint8 [K,n], its legal moves) are filled
+        when given.  step()'s other optional outputs (highest, episode statistics) are not produced: the env's
+        legal mask is refreshed at the end, episode statistics must not be enabled."""
         n = self.num_envs
         if self._step_counter is not None:
             raise G2048Error("step_many is not available with a device-side step counter")
         if self.ep_score is not None:
             raise G2048Error("step_many does not maintain episode statistics: build the env without 'episode'")
-        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device
-                and actions.is_contiguous() and actions.dim() == 2 and actions.shape[1] == n):
-            raise ValueError("actions must be a contiguous uint8 [K,%d] tensor on %s" % (n, self.device))
-        K = int(actions.shape[0])
+        flags = FLAG_AUTO_RESET if self.auto_reset else 0
+        if policy is None:
+            if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device
+                    and actions.is_contiguous() and actions.dim() == 2 and actions.shape[1] == n):
+                raise ValueError("actions must be a contiguous uint8 [K,%d] tensor on %s" % (n, self.device))
+            K = int(actions.shape[0])
+            if n_steps is not None and int(n_steps) != K:
+                raise ValueError("n_steps disagrees with actions.shape[0]")
+            if actions_out is not None:
+                raise ValueError("actions_out is only written when a policy draws the actions")
+        else:
+            if policy not in ("uniform", "legal"):
+                raise ValueError("policy must be None, 'uniform' or 'legal'")
+            if actions is not None or n_steps is None:
+                raise ValueError("with a policy pass n_steps and no actions")
+            K = int(n_steps)
+            flags |= _lib.FLAG_POLICY_LEGAL if policy == "legal" else _lib.FLAG_POLICY_UNIFORM
 
         def buf(t, dtype, shape, what):
             if t is None:
@@ -273,14 +291,20 @@ class BatchedGame2048:
             dones_u8 = torch.empty((K, n), dtype=torch.uint8, device=self.device)
         illegal = buf(illegal, torch.uint8, (K, n), "illegal")
         boards_traj = buf(boards_traj, torch.uint8, (K, n, 16), "boards_traj")
+        actions_out = buf(actions_out, torch.uint8, (K, n), "actions_out")
+        legal_mask_out = buf(legal_mask_out, torch.uint8, (K, n), "legal_mask_out")
         a = StepManyArgs(self._ptr(self.boards), self._ptr(actions), self._ptr(rewards), self._ptr(dones_u8),
                          self._ptr(illegal), self._ptr(boards_traj), n, self.env_id_base, self.seed, self.step_index,
-                         K, self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0)
+                         K, self.illegal_move_reward, self.max_tile_exp, flags, self._ptr(actions_out),
+                         self._ptr(legal_mask_out))
         if K:
             self._launch(self.lib.g2048_step_many, C.byref(a))
             self.step_index += K
             if self.legal_mask is not None:
-                self.status(legal_mask=self.legal_mask)
+                if legal_mask_out is not None:
+                    self.legal_mask.copy_(legal_mask_out[K - 1])
+                else:
+                    self.status(legal_mask=self.legal_mask)
         return rewards, dones_u8.view(torch.bool)
 
     def sample_actions(self, legal=False, out=None):

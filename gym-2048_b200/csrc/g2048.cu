@@ -505,6 +505,8 @@ struct ManyParams {
   uint8_t* dones;               // [n_steps][row_stride]
   uint8_t* illegal;             // nullable, [n_steps][row_stride]
   uint4* boards_traj;           // nullable, [n_steps][row_stride]: the board handed back after every step
+  uint8_t* actions_out;         // nullable, [n_steps][row_stride]: the actions a device policy chose
+  uint8_t* legal_mask;          // nullable, [n_steps][row_stride]: legal moves on the board handed back
   uint32_t n;                   // boards of this launch
   uint32_t n_steps;
   uint64_t row_stride;          // boards per step row of the [n_steps][...] arrays (>= n when the call was sliced)
@@ -512,12 +514,17 @@ struct ManyParams {
   uint32_t idx_lo;              // low half of the first step's index (nor 2^32 indices)
   uint32_t key;                 // stream_key(seed, step_index, env id, TAG_STEP)
   StreamKeys keys;              // k[1..9] of that key (k[0] is derived per step)
+  uint32_t policy_key;          // the same for TAG_POLICY (device policies)
+  StreamKeys policy_keys;
   float illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t flags;
 };
 
-template <bool EXTRAS>
+// POLICY 0: the actions are given.  1 / 2: the kernel plays g2048_sample_actions' uniform / random-legal policy
+// itself — the action of step k is drawn from the policy-tag stream at index step_index + k, for the legal policy
+// among the legal moves of the board the previous step handed back — so a whole random rollout is one launch.
+template <bool EXTRAS, int POLICY>
 __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_kernel(const ManyParams p) {
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
@@ -545,10 +552,17 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint4 bd = load_board(p.boards + i);
     size_t off = i;                                   // element (k, i) of the per-step arrays
-    uint32_t action = p.actions[off];
+    uint32_t action = POLICY ? 0u : p.actions[off];
+    uint32_t mask = POLICY == 2 ? legal_mask(bd.x, bd.y, bd.z, bd.w) : 15u;
     for (uint32_t k = 0; k < p.n_steps; ++k, off += p.row_stride) {
-      const uint32_t act = action & 3u;
-      if (k + 1u < p.n_steps) action = p.actions[off + p.row_stride];       // next step's action, one step ahead
+      uint32_t act;
+      if (POLICY) {
+        act = pick_action(mask, philox2x32_10_keys(p.env_lo + i, p.policy_key ^ (p.idx_lo + k), p.policy_keys).x0);
+        if (p.actions_out) p.actions_out[off] = (uint8_t)act;
+      } else {
+        act = action & 3u;
+        if (k + 1u < p.n_steps) action = p.actions[off + p.row_stride];     // next step's action, one step ahead
+      }
       uint32_t a, b, c, d;
       orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
       const Moved m = move_oriented(a, b, c, d, s_sel[4u + act]);
@@ -559,6 +573,11 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_
       if (EXTRAS) {
         if (p.illegal) p.illegal[off] = o.legal ? 0 : 1;
         if (p.boards_traj) p.boards_traj[off] = bd;
+        if (POLICY == 2 || p.legal_mask) {
+          const uint32_t lm = legal_mask(bd.x, bd.y, bd.z, bd.w);
+          if (p.legal_mask) p.legal_mask[off] = (uint8_t)lm;
+          if (POLICY == 2) mask = lm;                  // what the next step's draw chooses among
+        }
       }
     }
     p.boards[i] = bd;
@@ -933,17 +952,25 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
   return launch_check("g2048_step_kernel");
 }
 
+// lean, with optional outputs, uniform policy, random-legal policy
+static const void* const kManyKernels[4] = {
+    (const void*)g2048_step_many_kernel<false, 0>, (const void*)g2048_step_many_kernel<true, 0>,
+    (const void*)g2048_step_many_kernel<true, 1>, (const void*)g2048_step_many_kernel<true, 2>,
+};
+
 // One g2048_step_many launch: no 2^32 boundary of env ids or step indices inside.
 static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m, uint64_t k0, uint64_t ks,
                             cudaStream_t s) {
   ManyParams p;
   const uint64_t row0 = k0 * a->n + lo;
   p.boards = reinterpret_cast<uint4*>(a->boards) + lo;
-  p.actions = a->actions + row0;
+  p.actions = a->actions ? a->actions + row0 : nullptr;
   p.rewards = a->rewards + row0;
   p.dones = a->dones + row0;
   p.illegal = a->illegal ? a->illegal + row0 : nullptr;
   p.boards_traj = a->boards_traj ? reinterpret_cast<uint4*>(a->boards_traj) + row0 : nullptr;
+  p.actions_out = a->actions_out ? a->actions_out + row0 : nullptr;
+  p.legal_mask = a->legal_mask ? a->legal_mask + row0 : nullptr;
   p.n = (uint32_t)m;
   p.n_steps = (uint32_t)ks;
   p.row_stride = a->n;
@@ -952,6 +979,8 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
   p.idx_lo = (uint32_t)idx0;
   p.key = stream_key(a->seed, idx0, env0, TAG_STEP);
   make_stream_keys(p.key, 0u, p.keys);
+  p.policy_key = stream_key(a->seed, idx0, env0, TAG_POLICY);
+  make_stream_keys(p.policy_key, 0u, p.policy_keys);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = a->flags;
@@ -975,16 +1004,17 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != prepared_dev) {
-      cudaFuncSetAttribute(g2048_step_many_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(g2048_step_many_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(g2048_step_many_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
-      cudaFuncSetAttribute(g2048_step_many_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      for (const void* k : kManyKernels) {
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+      }
       prepared_dev = dev;
     }
   }
-  const bool extras = a->illegal || a->boards_traj;
-  const cudaError_t le = extras ? cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<true>, p)
-                                : cudaLaunchKernelEx(&cfg, g2048_step_many_kernel<false>, p);
+  const bool extras = a->illegal || a->boards_traj || a->legal_mask;
+  const int policy = (a->flags & G2048_FLAG_POLICY_LEGAL) ? 2 : (a->flags & G2048_FLAG_POLICY_UNIFORM) ? 1 : 0;
+  void* kargs[] = {&p};
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, kManyKernels[policy ? 1 + policy : (extras ? 1 : 0)], kargs);
   if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_many_kernel)");
   return G2048_OK;
 }
@@ -992,8 +1022,13 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
 int g2048_step_many(const G2048StepManyArgs* a, void* stream) {
   if (!a) return fail(G2048_ERR_INVALID, "g2048_step_many: args is NULL");
   if (a->n == 0 || a->n_steps == 0) return G2048_OK;
-  if (!a->boards || !a->actions || !a->rewards || !a->dones)
-    return fail(G2048_ERR_INVALID, "g2048_step_many: boards, actions, rewards and dones are required");
+  const bool has_policy = (a->flags & (G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL)) != 0u;
+  if ((a->flags & G2048_FLAG_POLICY_UNIFORM) && (a->flags & G2048_FLAG_POLICY_LEGAL))
+    return fail(G2048_ERR_INVALID, "g2048_step_many: choose one of G2048_FLAG_POLICY_UNIFORM / G2048_FLAG_POLICY_LEGAL");
+  if (!a->boards || !a->rewards || !a->dones || (!a->actions && !has_policy))
+    return fail(G2048_ERR_INVALID, "g2048_step_many: boards, rewards, dones and (without a policy flag) actions are required");
+  if (a->actions_out && !has_policy)
+    return fail(G2048_ERR_INVALID, "g2048_step_many: actions_out is only written under a policy flag");
   if (!aligned16(a->boards) || !aligned16(a->boards_traj))
     return fail(G2048_ERR_ALIGN, "g2048_step_many: boards / boards_traj must be 16-byte aligned");
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step_many: max_tile_exp %u > 63", a->max_tile_exp);

@@ -69,6 +69,9 @@ extern "C" {
 /* G2048StepArgs.flags */
 #define G2048_FLAG_AUTO_RESET 1u /* SB3 DummyVecEnv semantics: a terminated env is   */
                                  /* replaced by a fresh reset() board in the same step */
+/* g2048_step_many only: the kernel plays g2048_sample_actions' policy itself */
+#define G2048_FLAG_POLICY_UNIFORM 2u /* action uniform in {0,1,2,3} (train.py:119)        */
+#define G2048_FLAG_POLICY_LEGAL   4u /* uniform among the legal moves of the live board   */
 
 /* g2048_encode_obs dtype */
 #define G2048_OBS_U8   0
@@ -131,10 +134,16 @@ int g2048_step(const G2048StepArgs* args, void* stream);
  * the steps, so a step costs one action byte read and a reward and a done written
  * instead of 38 bytes, and there is one launch instead of n_steps.  The per-step
  * arrays are step-major: element (k, i) at k*n + i.
+ * With G2048_FLAG_POLICY_UNIFORM / _LEGAL the actions are not read but drawn in the
+ * kernel, exactly as g2048_sample_actions(legal mask of the live board, ..., step_index + k)
+ * would draw them before step k (policy-tag stream), and written to actions_out: a whole
+ * random rollout — `train.py:119`'s random agent, BASELINE config 4's random-legal play —
+ * is one launch.
  */
 typedef struct G2048StepManyArgs {
   uint8_t*       boards;       /* [n*16]         in/out: before the first / after the last step */
-  const uint8_t* actions;      /* [n_steps*n]    0..3; only the low 2 bits are read             */
+  const uint8_t* actions;      /* [n_steps*n]    0..3; only the low 2 bits are read; NULL with  */
+                               /*                a policy flag                                  */
   float*         rewards;      /* [n_steps*n]    out                                            */
   uint8_t*       dones;        /* [n_steps*n]    out                                            */
   uint8_t*       illegal;      /* [n_steps*n]    out, nullable                                  */
@@ -148,6 +157,9 @@ typedef struct G2048StepManyArgs {
   float          illegal_move_reward;
   uint32_t       max_tile_exp;
   uint32_t       flags;        /* G2048_FLAG_*                                                  */
+  uint8_t*       actions_out;  /* [n_steps*n]    out, nullable: the actions a policy flag drew  */
+  uint8_t*       legal_mask;   /* [n_steps*n]    out, nullable: bit d = move d legal on the     */
+                               /*                board handed back after the step               */
 } G2048StepManyArgs;
 
 int g2048_step_many(const G2048StepManyArgs* args, void* stream);

@@ -256,3 +256,48 @@ def test_step_many_is_k_steps(n, K, base, step0, kw):
         assert torch.equal(r.rewards, rewards[k]) and torch.equal(r.dones, dones[k]) and torch.equal(r.boards, traj[k])
     assert torch.equal(many.boards, traj[K - 1]) and torch.equal(lean.boards, many.boards)
     assert torch.equal(rewards_lean, rewards) and torch.equal(dones_lean, dones)
+
+
+@pytest.mark.parametrize("policy", ["uniform", "legal"])
+@pytest.mark.parametrize("n,K,base,step0,kw", [
+    (1000, 48, 77, 5, dict(illegal_move_reward=-1.0)),
+    (4096, 200, 0, 0, {}),                            # random-legal play reaches mid-game boards and natural deaths
+    (3000, 12, 2**32 - 1500, 2**32 - 4, dict(auto_reset=False)),
+])
+def test_step_many_device_policy_is_sample_actions_plus_step(policy, n, K, base, step0, kw):
+    """g2048_step_many with a policy flag == sample_actions() followed by step(), K times: against the oracle's
+    sampler and step (actions, rewards, dones, boards, legal masks) and against the product's two-kernel loop."""
+    import torch
+    import gym_2048_b200 as g
+    from oracle import oracle
+    seed = 99
+    legal = policy == "legal"
+    mk = lambda: g.BatchedGame2048(n, seed=seed, env_id_base=base, outputs=("legal_mask",),
+                                   illegal_move_reward=kw.get("illegal_move_reward", 0.0),
+                                   auto_reset=kw.get("auto_reset", True))
+    ref = oracle.OracleBatch(n, seed=seed, env_id_base=base, **kw)
+    ref.reset()
+    ref.step_index = step0
+    fused, loop = mk(), mk()
+    for game in (fused, loop):
+        game.reset()
+        game.step_index = step0
+    acts = torch.empty((K, n), dtype=torch.uint8, device="cuda")
+    masks = torch.empty((K, n), dtype=torch.uint8, device="cuda")
+    traj = torch.empty((K, n, 16), dtype=torch.uint8, device="cuda")
+    rewards, dones = fused.step_many(policy=policy, n_steps=K, actions_out=acts, legal_mask_out=masks, boards_traj=traj)
+    mask = oracle.status(ref.boards)["legal_mask"]
+    for k in range(K):
+        want = oracle.sample_actions(mask if legal else None, n, base, seed, step0 + k)
+        assert np.array_equal(acts[k].cpu().numpy(), want), k
+        o = ref.step(want)
+        mask = o["legal_mask"]
+        assert np.array_equal(rewards[k].cpu().numpy(), o["rewards"]), k
+        assert np.array_equal(dones[k].cpu().numpy().astype(np.uint8), o["dones"]), k
+        assert np.array_equal(traj[k].cpu().numpy(), ref.boards), k
+        assert np.array_equal(masks[k].cpu().numpy(), mask), k
+        a = loop.sample_actions(legal=legal)
+        assert torch.equal(a, acts[k])
+        r = loop.step(a)
+        assert torch.equal(r.boards, traj[k]) and torch.equal(r.rewards, rewards[k])
+    assert torch.equal(fused.boards, loop.boards) and torch.equal(fused.legal_mask, loop.legal_mask)
