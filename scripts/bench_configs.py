@@ -97,9 +97,24 @@ def c4(args):
     dt = timed(one, args.steps)
     empties = float((games[0].boards == 0).float().sum(1).mean())
     dtp = timed(policy_only, args.steps)
-    # the same loop as ONE CUDA graph per 8 steps is not possible with host-side step indices for the
-    # policy kernel; the per-step figure below is therefore bound by two Python-issued launches per step
-    return {"config": "c4", "workload": "262,144 envs, legal mask + auto-reset, random-legal policy on device, "
+    # the same play as one launch per 64 steps: the policy runs inside g2048_step_many (mask and action of
+    # every step still written out)
+    K = 64
+    lean = [g.BatchedGame2048(n, seed=42, device=DEV, env_id_base=s * n, outputs=("legal_mask",)) for s in range(2)]
+    for gm, src in zip(lean, games):
+        gm.set_boards(src.boards)
+    rew = torch.empty((K, n), dtype=torch.float32, device=DEV)
+    dn = torch.empty((K, n), dtype=torch.uint8, device=DEV)
+    ac = torch.empty((K, n), dtype=torch.uint8, device=DEV)
+    lm = torch.empty((K, n), dtype=torch.uint8, device=DEV)
+
+    def fused():
+        gm = lean[state["i"] % 2]
+        gm.step_many(policy="legal", n_steps=K, rewards=rew, dones=dn, actions_out=ac, legal_mask_out=lm)
+        state["i"] += 1
+    dtf = timed(fused, 40, warm=3) / K
+    return {"config": "c4", "fused_us_per_step": dtf * 1e6, "fused_env_steps_per_s": n / dtf,
+            "fused": "g2048_step_many with G2048_FLAG_POLICY_LEGAL, 64 steps per launch, actions + legal masks written every step", "workload": "262,144 envs, legal mask + auto-reset, random-legal policy on device, "
                                           "8 env sets round-robin, mid-game boards",
             "us_per_step_policy_plus_step": dt * 1e6, "env_steps_per_s": n / dt,
             "us_policy_kernel_only": dtp * 1e6, "us_step_kernel_by_difference": (dt - dtp) * 1e6,
