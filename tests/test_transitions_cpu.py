@@ -114,6 +114,38 @@ def test_csv_errors_are_reported_not_thrown(tmp_path):
     assert L.g2048_csv_rows(str(short).encode(), C.byref(n), C.byref(has)) == -1
 
 
+def test_csv_number_forms_round_trip(tmp_path):
+    """The importer's own number parsing (integers by hand, '%f' of integral values by hand, everything else
+    through strtod): fractional, negative, huge and exponent-form rewards, signs and '\r\n' line ends."""
+    L = g._lib.lib()
+    rewards = np.array([0.0, 4.0, -1.0, -0.5, 0.25, 2064.0, 1e15, 123456789012345.0, 3.999999, 1e-6, -123456.789012])
+    n = len(rewards)
+    rng = np.random.default_rng(2)
+    b = rng.integers(0, 18, (n, 16)).astype(np.uint8)
+    nb = rng.integers(0, 18, (n, 16)).astype(np.uint8)
+    a = rng.integers(0, 4, n).astype(np.uint8)
+    d = rng.integers(0, 2, n).astype(np.uint8)
+    path = str(tmp_path / "forms.csv")
+    assert L.g2048_csv_export(path.encode(), _p(b), _p(a), _p(rewards), _p(nb), _p(d), None, n, 0) == 0
+    txt = open(path).read()
+    assert txt.splitlines()[1:] == [("%d," * 17 + "%f," + "%d," * 16 + "%i") %
+                                    (*[(1 << int(e)) if e else 0 for e in b[i]], a[i], rewards[i],
+                                     *[(1 << int(e)) if e else 0 for e in nb[i]], d[i]) for i in range(n)]
+    # hand-edited forms a spreadsheet or another writer would produce
+    lines = txt.splitlines()
+    lines[2] = lines[2].replace(",4.000000,", ",+4.0e0,")
+    lines[3] = lines[3].replace(",-1.000000,", ",-1,")
+    open(path, "w").write("\r\n".join(lines) + "\r\n")
+    b2, nb2 = np.zeros_like(b), np.zeros_like(nb)
+    a2, d2, r2 = np.zeros_like(a), np.zeros_like(d), np.zeros(n)
+    cnt, has = C.c_uint64(0), C.c_int(0)
+    assert L.g2048_csv_rows(path.encode(), C.byref(cnt), C.byref(has)) == 0 and cnt.value == n
+    rc = L.g2048_csv_import(path.encode(), _p(b2), _p(a2), _p(r2), _p(nb2), _p(d2), None, n)
+    assert rc == 0, L.g2048_last_error()
+    assert np.array_equal(b2, b) and np.array_equal(nb2, nb) and np.array_equal(a2, a) and np.array_equal(d2, d)
+    assert np.array_equal(r2, np.array([float("%f" % v) for v in rewards]))
+
+
 def test_oracle_sample_actions_is_uniform_over_the_allowed_set():
     n = 200000
     masks = np.random.default_rng(3).integers(0, 16, n).astype(np.uint8)
