@@ -63,11 +63,11 @@ constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 // The step kernels' own persistent shape.  One 1024-thread CTA per SM measured 1 % faster than two of 512
 // (12.23 vs 12.37 us per 1 Mi boards): with two CTAs the hardware scheduler favours the older one and the SM
 // spends the last third of the launch on the younger one's 16 warps alone (scripts/micro/timeline.cu).
-#ifndef G2048_STEP_THREADS
-#define G2048_STEP_THREADS 1024
+#ifndef G2048_STEP_THREADS            // (the TMA-ring build variant keeps 512 x 2: its ring is static shared memory)
+#define G2048_STEP_THREADS (G2048_TMA ? 512 : 1024)
 #endif
 #ifndef G2048_STEP_CTAS_PER_SM
-#define G2048_STEP_CTAS_PER_SM 1
+#define G2048_STEP_CTAS_PER_SM (G2048_TMA ? 2 : 1)
 #endif
 constexpr int kStepThreads = G2048_STEP_THREADS, kStepCtasPerSm = G2048_STEP_CTAS_PER_SM;
 static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");

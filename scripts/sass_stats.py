@@ -27,9 +27,15 @@ def main():
         t = ins.split()
         o = t[1] if t[0].startswith("@") else t[0]
         return o.split(".")[0]
-    # loop = last backward branch
-    loop_end = max(a for a, i in body if op(i) == "BRA" and re.search(r"0x([0-9a-f]+)", i) and int(re.search(r"BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", i).group(1), 16) < a and not i.endswith(hex(a)))
-    tgt = [int(re.search(r"0x([0-9a-f]+)\s*$", i).group(1), 16) for a, i in body if a == loop_end][0]
+    # the hot loop = the backward branch that spans the most instructions without enclosing another backward
+    # branch's whole loop plus code outside it (barrier spin loops are short; the epilogue is not in any loop)
+    back = []
+    for a, i in body:
+        m = re.search(r"BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)\s*$", i) if op(i) == "BRA" else None
+        if m and int(m.group(1), 16) < a:
+            back.append((a - int(m.group(1), 16), a, int(m.group(1), 16)))
+    inner = [b for b in back if not any(o is not b and b[2] <= o[2] and o[1] <= b[1] and o[0] > 64 for o in back)]
+    _, loop_end, tgt = max(inner if inner else back)
     loop = [(a, i) for a, i in body if tgt <= a <= loop_end]
     # forward branches inside loop define skippable blocks
     blocks = []
