@@ -244,8 +244,10 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
 }
 
 #ifndef G2048_PIPELINE       // 1: software-pipelined loop — the move half of board j+1 and the finishing half of
-#define G2048_PIPELINE 1     //    board j share one loop body (one straight-line block the scheduler interleaves);
-#endif                       //    -2 % against the plain loop in the same run (profiles/r01_variants_v2.log)
+#define G2048_PIPELINE 0     //    board j share one loop body (one straight-line block the scheduler interleaves).
+#endif                       //    It was 2 % ahead of the plain loop when it was written (512x2 CTAs, 32-entry reset
+                             //    table); with the fresh-board table and one 1024-thread CTA per SM the plain loop is
+                             //    2 % ahead (11.99 vs 12.22 us, profiles/r01_variants_v2.log), so the plain loop ships.
 // Tried on top of this loop and dropped, both bit-exact and both slower because the kernel is issue-bound and every
 // extra instruction costs more than the memory system gives back (same log): warps claiming 32-board tiles from a
 // per-CTA shared-memory counter so that no warp runs out of work early (13.7 us vs 12.4 us: +30 instructions per
