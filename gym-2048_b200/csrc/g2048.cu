@@ -34,8 +34,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // ------------------------------------------------------------------------------------
-// launch geometry: 256-thread CTAs, grid-stride, at most kCtasPerSm resident CTAs per SM
-// so large batches run as one persistent wave over the 148 SMs.
+// launch geometry: grid-stride kernels in one persistent wave over the SMs — kThreads-wide CTAs,
+// kCtasPerSm of them per SM (four for the low-register streaming kernels, grid_for_streaming); the
+// step kernels have their own shape (kStepThreads x kStepCtasPerSm, shape_for).
 // ------------------------------------------------------------------------------------
 // Tunables (overridable with -D for scripts/kernel_variants.py experiments)
 #ifndef G2048_CTAS_PER_SM
@@ -52,7 +53,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 #endif
 #ifndef G2048_TMA            // 1: boards and actions reach the SM through a shared-memory ring filled by bulk async
 #define G2048_TMA 0          //    copies (TMA) under mbarriers; 0: per-thread LDG.128 one iteration ahead.
-#endif                       //    Measured (profiles/r01_variants.log): the ring is bit-exact but SLOWER, 15.2 us vs
+#endif                       //    Measured (profiles/r01_variants_v2.log): the ring is bit-exact but SLOWER, 15.2 us vs
                              //    12.4 us per 1 Mi boards with 2 to 5 stages alike — the per-thread loads were never
                              //    the limiter (the kernel is issue-bound) and the ring's barrier traffic adds ~40
                              //    instructions per board-warp.  Kept as a tested build variant, not shipped.
