@@ -116,6 +116,16 @@ static LaunchShape shape_for(uint64_t n, size_t static_smem) {
   return LaunchShape{(unsigned)ctas, block, budget > fixed ? (budget - fixed) / 1024 * 1024 : 0};
 }
 constexpr int kMaxPadSmem = 208 * 1024;
+// True the first time the calling thread asks for the current device under `seen` (one bit per device ordinal):
+// kernel attributes are per device and are set once, also for a host thread that drives several GPUs in turn.
+static bool first_use_on_current_device(uint64_t& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const uint64_t bit = 1ull << dev;
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}
 
 // ------------------------------------------------------------------------------------
 // kernels
@@ -875,10 +885,8 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   cfg.blockDim = dim3(shape.block);
   cfg.dynamicSmemBytes = shape.pad_smem;
   {
-    static thread_local int prepared_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != prepared_dev) {                       // once per device and thread: allow the padding, prefer shared memory
+    static thread_local uint64_t seen = 0;
+    if (first_use_on_current_device(seen)) {                       // once per device and thread: allow the padding, prefer shared memory
       cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
       cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
       cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
@@ -887,7 +895,6 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
       cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      prepared_dev = dev;
     }
   }
 #else
@@ -905,16 +912,13 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
 #if G2048_TMA
   // The staged kernel keeps a shared-memory ring per CTA: ask for a carveout that fits kCtasPerSm of them.
   {
-    static thread_local int prepared_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != prepared_dev) {
+    static thread_local uint64_t seen = 0;
+    if (first_use_on_current_device(seen)) {
       const int pct = 50;
       cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
       cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      prepared_dev = dev;
     }
   }
 #endif
@@ -1003,15 +1007,12 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
 #endif
   {
     // once per device and thread: allow the padding of shape_for, prefer shared memory over L1
-    static thread_local int prepared_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != prepared_dev) {
+    static thread_local uint64_t seen = 0;
+    if (first_use_on_current_device(seen)) {
       for (const void* k : kManyKernels) {
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
       }
-      prepared_dev = dev;
     }
   }
   const bool extras = a->illegal || a->boards_traj || a->legal_mask;
