@@ -942,6 +942,8 @@ int g2048_step(const G2048StepArgs* a, void* stream) {
     return fail(G2048_ERR_ALIGN,
                 "g2048_step: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned");
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
+  if (a->flags & ~G2048_FLAG_AUTO_RESET)
+    return fail(G2048_ERR_INVALID, "g2048_step: unknown flags 0x%x (the policy flags belong to g2048_step_many)", a->flags);
   if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   // The kernel treats the high half of the env id as launch-uniform (Philox head): a call whose
@@ -1036,6 +1038,8 @@ int g2048_step_many(const G2048StepManyArgs* a, void* stream) {
   if (!aligned16(a->boards) || !aligned16(a->boards_traj))
     return fail(G2048_ERR_ALIGN, "g2048_step_many: boards / boards_traj must be 16-byte aligned");
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step_many: max_tile_exp %u > 63", a->max_tile_exp);
+  if (a->flags & ~(G2048_FLAG_AUTO_RESET | G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL))
+    return fail(G2048_ERR_INVALID, "g2048_step_many: unknown flags 0x%x", a->flags);
   if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step_many: n must be < 2^32 - 256 per call");
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   // The kernel treats the high halves of the env id and of the step index as launch-uniform (they are folded

@@ -103,3 +103,31 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_argument_checks_that_need_no_gpu():
+    """Arguments are validated before anything touches the device: bad flags, missing pointers and alignment are
+    reported through the return code and g2048_last_error() on a box without a GPU too."""
+    L = g._lib.lib()
+    fake = 0x10000                      # never dereferenced: every call below fails validation first
+    a = g._lib.StepArgs()
+    a.boards, a.actions, a.rewards, a.dones, a.n = fake, fake, fake, fake, 8
+    a.flags = g._lib.FLAG_AUTO_RESET | g._lib.FLAG_POLICY_LEGAL
+    assert L.g2048_step(C.byref(a), None) == -1 and b"unknown flags" in L.g2048_last_error()
+    a.flags, a.max_tile_exp = g._lib.FLAG_AUTO_RESET, 64
+    assert L.g2048_step(C.byref(a), None) == -1 and b"max_tile_exp" in L.g2048_last_error()
+    a.max_tile_exp, a.boards = 0, fake + 4
+    assert L.g2048_step(C.byref(a), None) == -2 and b"16-byte aligned" in L.g2048_last_error()
+    a.boards, a.rewards = fake, None
+    assert L.g2048_step(C.byref(a), None) == -1 and b"required" in L.g2048_last_error()
+    m = g._lib.StepManyArgs()
+    m.boards, m.rewards, m.dones, m.n, m.n_steps = fake, fake, fake, 8, 4
+    assert L.g2048_step_many(C.byref(m), None) == -1 and b"actions are required" in L.g2048_last_error()
+    m.flags = g._lib.FLAG_POLICY_UNIFORM | g._lib.FLAG_POLICY_LEGAL
+    assert L.g2048_step_many(C.byref(m), None) == -1 and b"choose one" in L.g2048_last_error()
+    m.flags, m.actions, m.actions_out = 0, fake, fake
+    assert L.g2048_step_many(C.byref(m), None) == -1 and b"actions_out" in L.g2048_last_error()
+    m.actions_out, m.flags = None, 64
+    assert L.g2048_step_many(C.byref(m), None) == -1 and b"unknown flags" in L.g2048_last_error()
+    m.n_steps = 0                       # nothing to do is not an error
+    assert L.g2048_step_many(C.byref(m), None) == 0
