@@ -163,18 +163,9 @@ struct StepParams {
 // griddepcontrol.wait — it is constant data, so the copy overlaps the previous launch's tail — instead of
 // spending ~60 instructions per thread rebuilding it every launch.
 struct alignas(128) PairLut { Board4 e[1024]; };
-constexpr Board4 one_tile_board_c(uint32_t entry) {
-  const uint32_t cell = entry >> 1, v = ((entry & 1u) + 1u) << ((cell & 3u) * 8u), row = cell >> 2;
-  return Board4{row == 0 ? v : 0u, row == 1 ? v : 0u, row == 2 ? v : 0u, row == 3 ? v : 0u};
-}
 constexpr PairLut make_pair_lut() {
   PairLut t{};
-  for (uint32_t entry = 0; entry < 1024u; ++entry) {
-    const uint32_t k1 = entry >> 6, k2r = (entry >> 2) & 15u, t1 = (entry >> 1) & 1u, t2 = entry & 1u;
-    const uint32_t k2 = (k2r + ((k2r >= k1) ? 1u : 0u)) & 15u;
-    const Board4 b1 = one_tile_board_c(2u * k1 + t1), b2 = one_tile_board_c(2u * k2 + t2);
-    t.e[entry] = Board4{b1.x | b2.x, b1.y | b2.y, b1.z | b2.z, b1.w | b2.w};
-  }
+  for (uint32_t entry = 0; entry < 1024u; ++entry) t.e[entry] = two_tile_board(entry);
   return t;
 }
 __device__ const PairLut g_pair_lut = make_pair_lut();
@@ -271,7 +262,7 @@ __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4
 #define G2048_PTR_INC 0      //    kernel parameters (LDC) and re-deriving the addresses every iteration.  Measured:
 #endif                       //    smem selectors -1.2 %, pointer walk -0.7 %, both together -0.6 % -> selectors only
 
-constexpr int kStages = G2048_STAGES;
+[[maybe_unused]] constexpr int kStages = G2048_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

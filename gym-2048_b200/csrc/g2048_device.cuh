@@ -19,10 +19,12 @@
 #define G2048_DEV inline
 #define G2048_HD inline
 #define G2048_CONST static const
+#define G2048_HD_CONSTEXPR constexpr inline
 #else
 #define G2048_DEV __device__ __forceinline__
 #define G2048_HD __host__ __device__ __forceinline__
 #define G2048_CONST static __constant__      // one copy per translation unit (no relocatable device code)
+#define G2048_HD_CONSTEXPR __host__ __device__ constexpr      // also evaluated at compile time (the fresh-board table)
 #endif
 
 namespace g2048 {
@@ -373,7 +375,7 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
 // of 32 patterns (16 cells x {2,4}), kept as a uint4 table (shared memory in the kernels):
 // the fresh board is the OR of two entries.
 struct alignas(16) Board4 { uint32_t x, y, z, w; };
-G2048_DEV Board4 one_tile_board(uint32_t entry) {        // entry = cell * 2 + (tile == 4)
+G2048_HD_CONSTEXPR Board4 one_tile_board(uint32_t entry) {        // entry = cell * 2 + (tile == 4)
   const uint32_t cell = entry >> 1, v = ((entry & 1u) + 1u) << ((cell & 3u) * 8u), row = cell >> 2;
   return Board4{row == 0 ? v : 0u, row == 1 ? v : 0u, row == 2 ? v : 0u, row == 3 ? v : 0u};
 }
@@ -392,7 +394,7 @@ G2048_DEV void fresh_board(const Board4* lut, uint32_t w1, uint32_t w2, uint32_t
 // k1*64 + k2r*4 + t1*2 + t2, k1 = cell of the first tile, k2r = rank of the second tile's cell among
 // the 15 cells left (the table builder skips k1), t = 1 for a 4.  1024 entries (k2r = 15 unused),
 // 16 KB of shared memory: half the instructions of fresh_board in the reset path of the step kernel.
-G2048_DEV Board4 two_tile_board(uint32_t entry) {
+G2048_HD_CONSTEXPR Board4 two_tile_board(uint32_t entry) {
   const uint32_t k1 = entry >> 6, k2r = (entry >> 2) & 15u, t1 = (entry >> 1) & 1u, t2 = entry & 1u;
   const uint32_t k2 = (k2r + ((k2r >= k1) ? 1u : 0u)) & 15u;
   const Board4 b1 = one_tile_board(2u * k1 + t1), b2 = one_tile_board(2u * k2 + t2);

@@ -177,3 +177,21 @@ extern "C" int sim_sample_actions(const uint8_t* mask, uint8_t* actions, uint64_
   }
   return 0;
 }
+
+// reset through the 1024-entry fresh-board table (what the step kernels read) and through the 32-entry
+// one-tile table (reset kernel, oracle-checked): boards_pairs / boards_lut, 16 bytes each
+extern "C" int sim_fresh_boards(const uint32_t* w1, const uint32_t* w2, uint8_t* boards_pairs, uint8_t* boards_lut,
+                                uint64_t n) {
+  static Board4 table[1024];
+  static bool init = false;
+  if (!init) { for (uint32_t e = 0; e < 1024; ++e) table[e] = two_tile_board(e); init = true; }
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r[4];
+    fresh_board_pairs(table, w1[i], w2[i], r[0], r[1], r[2], r[3]);
+    store(boards_pairs + 16 * i, r);
+    fresh_board(lut(), w1[i], w2[i], r[0], r[1], r[2], r[3]);
+    store(boards_lut + 16 * i, r);
+  }
+  return 0;
+}
+

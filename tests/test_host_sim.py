@@ -94,3 +94,24 @@ def test_draw_words_all_forms():
         class Ops:
             draw_words = staticmethod(lambda n, base, seed, idx, tag, form=form: SimOps.draw_words(n, base, seed, idx, tag, form))
         pc.check_draw_words(Ops)
+
+
+def test_fresh_board_table_equals_two_spawns():
+    """The 1024-entry fresh-board table of the step kernels (two_tile_board, also evaluated at compile time for
+    the device constant) gives the board the two reset spawns give, for every cell pair and tile pair."""
+    import ctypes as C
+    import numpy as np
+    from backends import sim_lib, _p
+    rng = np.random.default_rng(3)
+    n = 400000
+    w1 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    w2 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    w1[:8] = [0, 0xFFFFFFFF, 0xF0000000, 0x0FFFFFFF, 0xE6666666, 0xE6666667, 0x10000000, 0x80000000]
+    w2[:8] = [0xFFFFFFFF, 0, 0xFFFFFFFF, 0x11111111, 0xFFFFFFFF, 0, 0xEEEEEEEE, 0x77777777]
+    a, b = np.zeros((n, 16), np.uint8), np.zeros((n, 16), np.uint8)
+    sim_lib().sim_fresh_boards(_p(w1), _p(w2), _p(a), _p(b), C.c_uint64(n))
+    assert np.array_equal(a, b)
+    assert np.all((a != 0).sum(axis=1) == 2) and set(np.unique(a)) == {0, 1, 2}
+    seen = {(tuple(np.flatnonzero(r)), tuple(r[r != 0])) for r in a[:200000]}
+    assert len(seen) == 16 * 15 // 2 * 4                        # every cell pair with every tile pair occurs
+
