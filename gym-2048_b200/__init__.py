@@ -27,4 +27,8 @@ __all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Ga
            "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS",
            "Transitions", "TransitionRecorder", "RolloutCollector", "gae_reference", "evaluate_model",
            "report_evaluation_results", "ResNetActorCritic"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+import os as _os
+if _os.environ.get("G2048_NO_REGISTER", "") != "1":      # like the reference's env/__init__.py:1-6: id '2048-v0' on import
+    register()

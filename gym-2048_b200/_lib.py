@@ -90,18 +90,34 @@ def _stale():
 
 def build(force=False, verbose=False):
     """Compile csrc/g2048.cu for sm_100a into gym-2048_b200/libg2048.so (nvcc cross-compiles
-    without a GPU).  Returns the path."""
+    without a GPU).  Returns the path.
+
+    Safe under torchrun on a fresh checkout: the build runs under an exclusive file lock (the ranks that
+    lose the race wait and find the library up to date), nvcc links into a temporary file in the same
+    directory and the result is moved into place atomically, so no process can dlopen a half-written file."""
     if not force and not _stale():
         return SO_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise G2048Error("nvcc not found: cannot build %s" % SO_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + SOURCES
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise G2048Error("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
-    if verbose:
-        print(r.stderr)
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():          # another process built it while we waited
+                return SO_PATH
+            tmp = "%s.tmp.%d" % (SO_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise G2048Error("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 

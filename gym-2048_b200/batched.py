@@ -219,10 +219,12 @@ class BatchedGame2048:
         a.step_index = self.step_index
         a.boards = self.boards.data_ptr()
         a.boards_out = None if boards_out is None else self._check_board_buffer(boards_out, "boards_out").data_ptr()
+        # every per-call pointer of the cached struct is reassigned on every call: a stale terminal_out would
+        # keep the kernel writing into a buffer its owner (e.g. a dropped TransitionRecorder) may have freed
         if terminal_out is not None:
             a.terminal_boards = self._check_board_buffer(terminal_out, "terminal_out").data_ptr()
-        elif self.terminal_boards is not None:
-            a.terminal_boards = self.terminal_boards.data_ptr()
+        else:
+            a.terminal_boards = None if self.terminal_boards is None else self.terminal_boards.data_ptr()
         fd = None
         if forced_draws is not None:
             fd = torch.as_tensor(forced_draws).to(self.device).contiguous()

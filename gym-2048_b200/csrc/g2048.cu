@@ -553,7 +553,9 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_
   mbar_wait(&s_lut_bar, 0u);
   const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
   const uint32_t n = p.n, stride = gridDim.x * blockDim.x;       // the CTA size is chosen at launch (see launch_step_many)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // (i_next > i: n may be as large as 2^32 - 257, so i + stride can wrap — the same guard as in g2048_step_kernel)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, i_next; i < n; i = i_next > i ? i_next : n) {
+    i_next = i + stride;
     uint4 bd = load_board(p.boards + i);
     size_t off = i;                                   // element (k, i) of the per-step arrays
     uint32_t action = POLICY ? 0u : p.actions[off];
@@ -1260,11 +1262,8 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   const uint64_t rest_chunks = lead ? e->n_chunks - 1 : e->n_chunks;
   uint64_t per = (n - lead + rest_chunks - 1) / rest_chunks;
   per = (per + 255) / 256 * 256;
-  int c = 0;
-  for (uint64_t lo = 0; lo < n; ++c) {
-    const uint64_t want = (c == 0 && lead) ? lead : per;
-    const uint64_t m = (n - lo < want) ? n - lo : want;
-    const cudaStream_t s = e->streams[c % e->n_streams];
+  // One slice: H2D(actions) -> step kernel -> D2H(results), all on stream s.
+  auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s) -> int {
     G2048_CUDA(cudaMemcpyAsync(e->d_actions + lo, actions_host + lo, m, cudaMemcpyHostToDevice, s));
     G2048StepArgs a;
     std::memset(&a, 0, sizeof a);
@@ -1292,6 +1291,24 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     if (o->illegal) G2048_CUDA(cudaMemcpyAsync(o->illegal + lo, e->d_illegal + lo, m, cudaMemcpyDeviceToHost, s));
     if (o->highest_exp) G2048_CUDA(cudaMemcpyAsync(o->highest_exp + lo, e->d_highest + lo, m, cudaMemcpyDeviceToHost, s));
     if (o->legal_mask) G2048_CUDA(cudaMemcpyAsync(o->legal_mask + lo, e->d_mask + lo, m, cudaMemcpyDeviceToHost, s));
+    return G2048_OK;
+  };
+  int c = 0;
+  for (uint64_t lo = 0; lo < n; ++c) {
+    const uint64_t want = (c == 0 && lead) ? lead : per;
+    const uint64_t m = (n - lo < want) ? n - lo : want;
+    const int rc = issue_slice(lo, m, e->streams[c % e->n_streams]);
+    if (rc) {
+      // Some slices of this step may already have run.  Drain the streams (no work of the failed call is left
+      // in flight over the caller's host buffers) and say that the env is no longer at a step boundary: the
+      // step index is NOT advanced and the boards are a mix of pre- and post-step slices — reset or
+      // g2048_env_set_boards_host before stepping again.
+      char first[sizeof g_err];
+      std::snprintf(first, sizeof first, "%s", g_err);
+      for (int i = 0; i < e->n_streams; ++i) cudaStreamSynchronize(e->streams[i]);
+      return fail(rc, "g2048_env_step_host: slice %d failed (%s); env state is indeterminate (boards [0,%llu) were "
+                      "stepped), step index not advanced", c, first, (unsigned long long)lo);
+    }
     lo += m;
   }
   e->step_index += 1;

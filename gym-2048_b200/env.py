@@ -323,11 +323,13 @@ class Game2048Env(_EnvBase):
         self.Matrix = new_board
 
 
-def register():
-    """Register '2048-v0' with gymnasium when it is installed (reference env/__init__.py:1-6)."""
+def register(force=False):
+    """Register '2048-v0' with gymnasium when it is installed (reference env/__init__.py:1-6, which does so
+    when the package is imported; `import gym_2048_b200` calls this too unless G2048_NO_REGISTER=1).
+    An id already taken — the reference package imported first — is left alone unless `force`."""
     if _gym is None:
         return False
     from gymnasium.envs.registration import register as _register, registry
-    if '2048-v0' not in registry:
+    if force or '2048-v0' not in registry:
         _register(id='2048-v0', entry_point='gym_2048_b200.env:Game2048Env')
     return True

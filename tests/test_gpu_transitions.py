@@ -187,3 +187,25 @@ def test_recorder_matches_oracle_rollout_in_game_order(G, tmp_path):
     rec.rewind()
     rec.step(game.sample_actions())
     assert rec.t == 1
+
+
+def test_plain_step_after_recorder_step_does_not_write_the_recorders_terminal_slice(G):
+    """the cached G2048StepArgs kept `terminal_boards` pointing at the recorder's [T,n,16] slice after a
+    step(terminal_out=...) on a game WITHOUT the 'terminal' output, so later plain step() calls kept writing
+    terminal boards into storage the recorder may have freed.  Every per-call pointer is now reassigned per call."""
+    import torch
+    n = 4096
+    game = G.BatchedGame2048(n, seed=5, outputs=("illegal",))          # no 'terminal' output of its own
+    game.reset()
+    rec = G.TransitionRecorder(game, horizon=2)
+    gen = torch.Generator(device=game.device).manual_seed(3)
+    rec.step(torch.randint(0, 4, (n,), generator=gen, device=game.device, dtype=torch.uint8))
+    assert game._args.terminal_boards == rec.terminal[0].data_ptr()
+    sentinel = 0xAB
+    rec.terminal.fill_(sentinel)
+    for _ in range(40):                                                # ~7 % of the envs end per step: plenty of terminal boards
+        r = game.step(torch.randint(0, 4, (n,), generator=gen, device=game.device, dtype=torch.uint8))
+        assert r.terminal_boards is None
+    assert game._args.terminal_boards is None
+    torch.cuda.synchronize()
+    assert bool((rec.terminal == sentinel).all()), "a plain step() wrote into the recorder's terminal slice"
