@@ -157,7 +157,6 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    config = workload_config(args, world=args.gpus)
     K, W = max(args.steps, 1), max(args.warmup, 0)
     if reference_available():
         kind = "reference"
@@ -167,6 +166,10 @@ def run_reference(args):
         dt = cores * per * K / value
         sample = "%d processes x 1 unmodified reference env x %d step() calls per bench step, uniform-random " \
                  "actions, reset() on terminated" % (cores, per)
+        ran = {"workload": "%d single 4x4 reference envs (unmodified Game2048Env.step incl. stack()), one per host "
+                           "core, uniform-random actions, reset() on terminated — the reference has no batched form" % cores,
+               "envs": cores, "envs_per_process": 1, "processes": cores, "step_calls_per_bench_step": cores * per,
+               "parallelism": "multiprocessing, one env per process"}
     else:
         kind = "port"
         n = 1 << 18
@@ -179,11 +182,15 @@ def run_reference(args):
         dt = (time.perf_counter() - t0) * K / reps
         value = n * 4 * K / dt
         sample = "C oracle port, %d threads, %d envs x 4 steps per bench step" % (cores, n)
+        ran = {"workload": "C oracle port of the reference step(), %d envs stepped by %d threads" % (n, cores),
+               "envs": n, "threads": cores}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": config,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        # `config` names the benchmark both arms are quoted on (the GPU arm's: BASELINE config 3); what THIS arm
+        # executed on the host cores — it has no batched form — is `reference_workload`
+        "config": workload_config(args, world=args.gpus), "reference_workload": ran,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "cpu": host_cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,13 +254,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(args, world):
-    per_gpu = args.envs if args.scaling == "weak" else args.envs // world
-    return {"workload": "BASELINE config 3: %d parallel 4x4 envs per GPU, uniform-random actions, auto-reset"
-                        % per_gpu,
-            "envs_per_gpu": per_gpu, "global_envs": per_gpu * world, "parallelism": "independent slices x%d" % world,
-            "l2_policy": "%d independent env sets stepped round-robin (working set > 126 MB L2)" % args.sets,
-            "sets": args.sets, "outputs": "boards,rewards,dones (lean kernel)"}
+def workload_config(args, world, scaling=None, issue=None):
+    scaling = scaling or args.scaling
+    per_gpu = args.envs if scaling == "weak" else args.envs // world
+    cfg = {"workload": "BASELINE config 3: %d parallel 4x4 envs in total, sharded as %d contiguous slices of %d "
+                       "(one per GPU), uniform-random actions, auto-reset" % (per_gpu * world, world, per_gpu),
+           "envs_per_gpu": per_gpu, "global_envs": per_gpu * world, "parallelism": "independent slices x%d" % world,
+           "l2_policy": "%d independent env sets stepped round-robin, one launch per set per step: %.0f MB of "
+                        "algorithmic traffic per GPU between two visits of a set (> 126 MB L2)"
+                        % (args.sets, args.sets * per_gpu * ALG_BYTES_PER_STEP / 1e6),
+           "sets": args.sets, "outputs": "boards,rewards,dones (lean kernel)"}
+    if issue:
+        cfg["issue"] = issue
+    return cfg
 
 
 def hbm_peak():
@@ -264,14 +277,76 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(n):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture, scaled to n."""
+def committed_ncu_traffic(n):
+    """DRAM bytes per launch of the step kernel from the COMMITTED ncu capture (profiles/step_kernel_traffic.json),
+    scaled to n boards — a static figure, not a measurement of this run."""
     try:
         with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
             t = json.load(f)
-        return t["dram_bytes_per_board"] * n
+        return t["dram_bytes_per_board"] * n, t.get("source", "profiles/step_kernel_traffic.json"), \
+            t.get("kind", "dram__bytes_read.sum + dram__bytes_write.sum, ncu (cold cache, serialised launches)")
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None, None
+
+
+def state_checksum(torch, dist, games, total_envs, rank, n, world, dev):
+    """64-bit checksum of every board of every env set, keyed by the GLOBAL env id: independent of how the batch
+    is sharded (sum over ranks), so a strong-scaling run must print the same value for N = 1, 2, 4, 8."""
+    acc = torch.zeros(2, dtype=torch.int64, device=dev)
+    ids = torch.arange(n, dtype=torch.int64, device=dev)
+    for s, gm in enumerate(games):
+        w = gm.boards.view(torch.int64).view(n, 2)
+        gid = ids + (s * total_envs + rank * n)
+        h = ((w[:, 0] * -7046029254386353131) ^ w[:, 1]) * (2 * gid + 1)          # int64 arithmetic wraps
+        acc[0] += (h & 0xFFFFFFFF).sum()
+        acc[1] += ((h >> 32) & 0xFFFFFFFF).sum()
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    lo, hi = int(acc[0].item()), int(acc[1].item())
+    return "%016x" % ((lo + (hi << 32)) & (2**64 - 1))
+
+
+def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, max_over_ranks_vec):
+    """Spin-up, warm-up and R back-to-back timed regions of K step launches each, round-robin over `games`.
+    Returns (region times in ms, max over ranks, per region; issue description; t_start, t_end)."""
+    S, P = len(games), pool.shape[0]
+    total = spinup + W + R * K
+    if small:
+        # a shard the GPU steps faster than Python can launch: the whole schedule is built up front and each
+        # region is ONE C call that issues its K launches (g2048_step_list)
+        sched = g.StepSchedule()
+        for j in range(total):
+            sched.add(games[j % S], pool[j % P])
+        sched.build()
+        issue = "g2048_step_list via StepSchedule (K launches per C call; one kernel launch per env step)"
+
+        def run(lo, hi):
+            sched.run(lo, hi)
+    else:
+        issue = "BatchedGame2048.step() from a Python loop (one kernel launch per env step)"
+
+        def run(lo, hi):
+            for j in range(lo, hi):
+                games[j % S].step(pool[j % P])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    torch.cuda.synchronize()
+    barrier()
+    # no host sleep, synchronisation or barrier between the spin-up, the warm-up and the timed regions: the
+    # clocks and the launch pipeline are in steady state when the first event is recorded
+    run(0, spinup)
+    run(spinup, spinup + W)
+    t_start = time.perf_counter()
+    ev[0].record()
+    at = spinup + W
+    for r in range(R):
+        run(at, at + K)
+        at += K
+        ev[r + 1].record()
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    barrier()
+    ms = [ev[r].elapsed_time(ev[r + 1]) for r in range(R)]
+    return max_over_ranks_vec(ms), issue, t_start, t_end
 
 
 def run_ours(args):
@@ -301,42 +376,68 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def max_over_ranks_vec(xs):
+        t = torch.tensor(xs, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    K, W, R, S = args.steps, args.warmup, args.repeats, args.sets
+    lib = g._lib.lib()
+
+    def make_workload(n, total_envs):
+        """S env sets of n boards (global ids: set s, rank r -> s*total + r*n ...), boards produced by the env itself
+        (reset + 6 real steps), and a pool of uniform-random action rows drawn on the device from the library's
+        policy stream — a function of the GLOBAL env id, so the workload does not depend on the sharding."""
+        games = [g.BatchedGame2048(n, seed=42, device=dev, env_id_base=s * total_envs + rank * n, outputs=())
+                 for s in range(S)]
+        pool = torch.empty((args.action_pool, n), dtype=torch.uint8, device=dev)
+        for t in range(args.action_pool):
+            g._lib.check(lib.g2048_sample_actions(None, pool[t].data_ptr(), n, rank * n, 1234, t,
+                                                  torch.cuda.current_stream(dev).cuda_stream))
+        for gm in games:
+            gm.reset()
+            for t in range(6):
+                gm.step(pool[t % args.action_pool])
+        torch.cuda.synchronize()
+        return games, pool
+
+    # ---- headline: BASELINE config 3 at this N (strong: args.envs boards in total; weak: per GPU) ----------
     n = args.envs if args.scaling == "weak" else args.envs // world
     total_envs = n * world
-    K, W, R = args.steps, args.warmup, args.sets
-    # R independent batches; global env ids are disjoint across sets and ranks
-    games = [g.BatchedGame2048(n, seed=42, device=dev, env_id_base=s * total_envs + rank * n, outputs=())
-             for s in range(R)]
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = torch.randint(0, 4, (args.action_pool, n), generator=gen, device=dev, dtype=torch.uint8)
-    for gm in games:                       # boards generated by the env itself: reset + a few real steps
-        gm.reset()
-        for t in range(6):
-            gm.step(pool[t % args.action_pool])
-    torch.cuda.synchronize()
-
+    small = n < args.small_below
+    games, pool = make_workload(n, total_envs)
     sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(W):
-        games[i % R].step(pool[i % args.action_pool])
-    torch.cuda.synchronize()
     if sampler:
-        sampler.wait_first_sample()
-    barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t_start = time.perf_counter()
-    start.record()
-    for i in range(K):
-        games[i % R].step(pool[i % args.action_pool])
-    end.record()
-    torch.cuda.synchronize()
-    t_end = time.perf_counter()
-    barrier()
-    dev_ms = start.elapsed_time(end)
-    ms = max_over_ranks(dev_ms)
-    clocks = sampler.stop(t_start, t_end) if sampler else None
+        sampler.wait_first_sample()            # BEFORE the spin-up: nothing sleeps between warm-up and the clock
+    t_spin = time.perf_counter()
+    region_ms, issue, t_start, t_end = time_step_regions(torch, g, games, pool, args.spinup, W, K, R, small, barrier,
+                                                         max_over_ranks_vec)
+    clocks = sampler.stop(t_spin, t_end) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "spin-up + warm-up + timed regions (contiguous step launches)"
+    ms = statistics.median(region_ms)
     value = total_envs * K / (ms * 1e-3)
-    launch_s = ms * 1e-3 / K              # the region holds only step-kernel launches, back to back
+    launch_s = ms * 1e-3 / K              # a region holds only step-kernel launches, back to back
+    checksum = state_checksum(torch, dist, games, total_envs, rank, n, world, dev)
+
+    # ---- weak-scaling extra at N > 1 (args.envs boards PER GPU): what round 1's SCALE file measured ---------
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        del games, pool
+        torch.cuda.empty_cache()
+        nw = args.envs
+        wg, wp = make_workload(nw, nw * world)
+        w_ms, w_issue, _, _ = time_step_regions(torch, g, wg, wp, max(args.spinup // 8, 256), W, K, max(R // 2, 5),
+                                                nw < args.small_below, barrier, max_over_ranks_vec)
+        wm = statistics.median(w_ms)
+        weak = {"scaling": "weak", "envs_per_gpu": nw, "global_envs": nw * world, "value": nw * world * K / (wm * 1e-3),
+                "unit": UNIT, "ms_per_step": wm / K, "repeats": len(w_ms),
+                "roofline_frac": ALG_BYTES_PER_STEP * nw / (wm * 1e-3 / K) / 1e9 / hbm_peak()[0], "issue": w_issue}
+        games, pool = wg, wp
+        n_f, total_f = nw, nw * world
+    else:
+        n_f, total_f = n, total_envs
 
     # ---- several steps per launch (g2048_step_many): the same steps with the boards held in registers in
     #      between — the open-loop form of this workload (the actions are pre-generated).  Reported beside the
@@ -344,34 +445,37 @@ def run_ours(args):
     fused = None
     if args.fused_steps > 0:
         Kf = args.fused_steps
-        facts = torch.randint(0, 4, (Kf, n), generator=gen, device=dev, dtype=torch.uint8)
-        frew = torch.empty((Kf, n), dtype=torch.float32, device=dev)
-        fdone = torch.empty((Kf, n), dtype=torch.uint8, device=dev)
-        launches = max(2, min(200, (1 << 31) // (Kf * n)))
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        facts = torch.randint(0, 4, (Kf, n_f), generator=gen, device=dev, dtype=torch.uint8)
+        frew = torch.empty((Kf, n_f), dtype=torch.float32, device=dev)
+        fdone = torch.empty((Kf, n_f), dtype=torch.uint8, device=dev)
+        launches = max(2, min(200, (1 << 31) // (Kf * n_f)))
         for i in range(2):
-            games[i % R].step_many(facts, rewards=frew, dones=fdone)
+            games[i % S].step_many(facts, rewards=frew, dones=fdone)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         f0.record()
         for i in range(launches):
-            games[i % R].step_many(facts, rewards=frew, dones=fdone)
+            games[i % S].step_many(facts, rewards=frew, dones=fdone)
         f1.record()
         torch.cuda.synchronize()
         f_ms = max_over_ranks(f0.elapsed_time(f1))
-        fused = {"api": "g2048_step_many", "steps_per_launch": Kf, "launches": launches,
-                 "value": total_envs * Kf * launches / (f_ms * 1e-3), "unit": UNIT,
+        fused = {"api": "g2048_step_many", "steps_per_launch": Kf, "launches": launches, "envs_per_gpu": n_f,
+                 "value": total_f * Kf * launches / (f_ms * 1e-3), "unit": UNIT,
                  "us_per_step": f_ms * 1e3 / (Kf * launches),
                  "algorithmic_bytes_per_step": 6 + 32.0 / Kf,
                  "note": "bit-identical to steps_per_launch calls of step(); boards stay in registers between steps"}
         del facts, frew, fdone
+    del games, pool
+    torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through the C-ABI handle, copies inside the timed region ----------
-    Ke = max(3, min(K, args.e2e_steps))
+    Ke = max(3, min(K * R, args.e2e_steps))
     henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, n_chunks=args.e2e_chunks)
     henv.reset()
     host_pool = torch.randint(0, 4, (8, n), dtype=torch.uint8).pin_memory()
-    for i in range(3):
+    for i in range(5):
         henv.step_pinned(host_pool[i % 8])
     barrier()
     t0 = time.perf_counter()
@@ -390,20 +494,28 @@ def run_ours(args):
 
     peak, peak_src = hbm_peak()
     achieved = ALG_BYTES_PER_STEP * n / launch_s / 1e9
-    traffic = measured_traffic(n)
+    traffic, traffic_src, traffic_kind = committed_ncu_traffic(n)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "repeats": R,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+        "timing": {"issue": issue, "statistic": "median over `repeats` back-to-back regions of `steps` launches (CUDA events on the "
+                                "launching stream, max over ranks per region)",
+                   "spinup_launches": args.spinup, "ms_per_step_min": min(region_ms) / K,
+                   "ms_per_step_max": max(region_ms) / K, "ms_per_step_mean": statistics.fmean(region_ms) / K},
+        "state_checksum": checksum,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "g2048_step_kernel<false, false>",
+                     "frac_definition": "algorithmic bytes (38 B per board-step, SURVEY 8d) / launch time / peak",
+                     "traffic": traffic, "traffic_source": traffic_src, "traffic_kind": traffic_kind,
+                     "peak_source": peak_src, "kernel": "g2048_step_kernel<0, false>",
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n,
                      "launch_us": launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,
                 "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "chunks": args.e2e_chunks,
                 "api": "g2048_env_step_host (pinned host buffers)", "checksum": chk},
+        "weak": weak,
         "fused": fused,
-        "gpu_launches": K, "e2e_gpu_launches": e2e_launches,
+        "gpu_launches": K * R, "e2e_gpu_launches": e2e_launches,
         "clocks": clocks,
         "gpu": torch.cuda.get_device_name(local),
     }
@@ -432,12 +544,19 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=None, help="K: step launches per timed region")
+    ap.add_argument("--warmup", type=int, default=None, help="W: untimed launches right before the first region")
+    ap.add_argument("--repeats", type=int, default=25, help="R: back-to-back timed regions; the median is reported")
+    ap.add_argument("--spinup", type=int, default=16384,
+                    help="untimed step launches before the warm-up (clock/power ramp; fixed, so the state "
+                         "checksum does not depend on N)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--envs", type=int, default=1 << 20, help="boards per GPU (weak) or in total (strong)")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
-    ap.add_argument("--sets", type=int, default=8)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="boards in total (strong, BASELINE config 3) or per GPU (weak)")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra block at N > 1")
+    ap.add_argument("--sets", type=int, default=32)
+    ap.add_argument("--small-below", type=int, default=148 * 1024,
+                    help="shards smaller than this are issued through g2048_step_list (K launches per C call)")
     ap.add_argument("--action-pool", type=int, default=16)
     ap.add_argument("--fused-steps", type=int, default=32, help="steps per g2048_step_many launch (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=200)
@@ -450,8 +569,9 @@ def main():
         args.steps = 20 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else args.warmup
         return run_reference(args)
-    args.steps = 50000 if args.steps is None else args.steps
-    args.warmup = 200 if args.warmup is None else max(args.warmup, 3)
+    args.steps = 200 if args.steps is None else args.steps
+    args.warmup = 50 if args.warmup is None else max(args.warmup, 3)
+    args.repeats = max(args.repeats, 1)
     return run_ours(args)
 
 

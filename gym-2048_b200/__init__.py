@@ -1,7 +1,8 @@
 """gym-2048_b200 — B200-native batched 2048 environment (drop-in for rgal/gym-2048's env).
 
 Public surface:
-  BatchedGame2048   N boards on one GPU, one fused CUDA kernel per step (batched.py)
+  BatchedGame2048   N boards on one GPU, one fused CUDA kernel per step (batched.py); step_n / capture /
+                    StepSchedule issue many steps per interpreter trip (small batches are launch-bound)
   HostSteppedEnv    host-buffer handle of the C ABI (actions/results in pinned host memory)
   Game2048Env       single-env class with the reference's gymnasium + game API (env.py)
   Game2048VecEnv    Stable-Baselines3-style VecEnv adapter over BatchedGame2048 (vec_env.py)
@@ -14,7 +15,7 @@ CPU fallback.
 """
 from . import _lib
 from ._lib import G2048Error, build
-from .batched import ALL_OUTPUTS, BatchedGame2048, HostSteppedEnv, StepResult, shard_range, tile_to_exp
+from .batched import ALL_OUTPUTS, BatchedGame2048, HostSteppedEnv, StepResult, StepSchedule, shard_range, tile_to_exp
 from .stats import EpisodeStats
 from .env import Game2048Env, IllegalMove, register, stack
 from .vec_env import Game2048VecEnv
@@ -23,7 +24,7 @@ from .rollout import RolloutCollector, gae_reference
 from .evaluate import evaluate_model, report_evaluation_results
 from .policy import ResNetActorCritic
 
-__all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "Game2048Env", "Game2048VecEnv", "IllegalMove",
+__all__ = ["BatchedGame2048", "HostSteppedEnv", "StepResult", "StepSchedule", "Game2048Env", "Game2048VecEnv", "IllegalMove",
            "stack", "register", "shard_range", "tile_to_exp", "EpisodeStats", "build", "G2048Error", "ALL_OUTPUTS",
            "Transitions", "TransitionRecorder", "RolloutCollector", "gae_reference", "evaluate_model",
            "report_evaluation_results", "ResNetActorCritic"]

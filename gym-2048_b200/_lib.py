@@ -17,13 +17,13 @@ HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_PKG, "c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_AUTO_RESET = 1
 FLAG_POLICY_UNIFORM, FLAG_POLICY_LEGAL = 2, 4
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
-    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
+    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_n", "g2048_step_list", "g2048_one", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
@@ -49,7 +49,20 @@ class StepArgs(C.Structure):
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
+        ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
     ]
+
+
+class OneIO(C.Structure):
+    """G2048OneIO (include/g2048.h): the packed in/out block of g2048_one."""
+    _fields_ = [
+        ("values", C.c_int64 * 16), ("obs", C.c_int64 * 256), ("reward", C.c_float), ("score", C.c_uint32),
+        ("done", C.c_uint8), ("illegal", C.c_uint8), ("changed", C.c_uint8), ("highest_exp", C.c_uint8),
+        ("legal_mask", C.c_uint8), ("n_empty", C.c_uint8), ("is_end", C.c_uint8), ("bad_cells", C.c_uint8),
+    ]
+
+
+ONE_STEP, ONE_RESET, ONE_MOVE, ONE_ADD_TILE, ONE_STATUS = 0, 1, 2, 3, 4
 
 
 class StepManyArgs(C.Structure):
@@ -143,6 +156,9 @@ def lib():
     L.g2048_env_step_index.restype = C.c_uint64
     u64, vp, u32 = C.c_uint64, C.c_void_p, C.c_uint32
     L.g2048_step.argtypes = [C.POINTER(StepArgs), vp]
+    L.g2048_step_n.argtypes = [C.POINTER(StepArgs), u32, u64, vp]
+    L.g2048_step_list.argtypes = [vp, u64, vp]
+    L.g2048_one.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, u64, C.c_float, u32, vp, C.c_int]
     L.g2048_step_many.argtypes = [C.POINTER(StepManyArgs), vp]
     L.g2048_reset.argtypes = [vp, vp, u64, u64, u64, u64, vp]
     L.g2048_add_tile.argtypes = [vp, u64, u64, u64, u64, vp]

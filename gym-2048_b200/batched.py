@@ -56,6 +56,7 @@ class StepResult:
     terminal_boards: Optional[torch.Tensor] = None  # uint8 [n,16], valid where dones
     final_score: Optional[torch.Tensor] = None  # int32 [n] episode score, valid where dones
     final_len: Optional[torch.Tensor] = None    # int32 [n] episode length, valid where dones
+    final_return: Optional[torch.Tensor] = None  # float32 [n] sum of the episode's rewards (SB3 Monitor 'r'), where dones
 
 
 class BatchedGame2048:
@@ -100,6 +101,8 @@ class BatchedGame2048:
         self.ep_len = torch.zeros(n, **i32) if ep else None
         self.final_score = torch.zeros(n, **i32) if ep else None
         self.final_len = torch.zeros(n, **i32) if ep else None
+        self.ep_return = torch.zeros(n, dtype=torch.float32, device=dev) if ep else None
+        self.final_return = torch.zeros(n, dtype=torch.float32, device=dev) if ep else None
         self._step_counter = None      # device uint64 step index (use_device_step_counter)
         self._args = None              # cached G2048StepArgs, rebuilt when a knob changes
 
@@ -163,10 +166,12 @@ class BatchedGame2048:
             if m is None:
                 self.ep_score.zero_()
                 self.ep_len.zero_()
+                self.ep_return.zero_()
             else:
                 keep = (m == 0).to(torch.int32)
                 self.ep_score.mul_(keep)
                 self.ep_len.mul_(keep)
+                self.ep_return.mul_(keep.to(torch.float32))
         if self.legal_mask is not None:
             self.status(legal_mask=self.legal_mask)
         return self.boards
@@ -178,7 +183,8 @@ class BatchedGame2048:
                      self._ptr(self.terminal_boards), self._ptr(self.ep_score), self._ptr(self.ep_len),
                      self._ptr(self.final_score), self._ptr(self.final_len), None, self._ptr(self._step_counter),
                      self.num_envs, self.env_id_base, self.seed, self.step_index,
-                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0, None)
+                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0, None,
+                     self._ptr(self.ep_return), self._ptr(self.final_return))
         self._args = a
         self._args_ref = C.byref(a)
         self._args_key = (self.seed, self.env_id_base, self.illegal_move_reward, self.max_tile_exp,
@@ -186,7 +192,7 @@ class BatchedGame2048:
         self._result = StepResult(self.boards, self.rewards, self._dones.view(torch.bool),
                                   None if self._illegal is None else self._illegal.view(torch.bool),
                                   self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
-                                  self.final_len)
+                                  self.final_len, self.final_return)
 
     def _check_board_buffer(self, t, what):
         if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.device == self.device
@@ -241,6 +247,86 @@ class BatchedGame2048:
         res.boards = self.boards
         res.terminal_boards = terminal_out if terminal_out is not None else self.terminal_boards
         return res
+
+    def step_n(self, actions, rewards=None, dones=None, illegal=None, highest_exp=None, legal_mask_out=None):
+        """K consecutive steps, ONE KERNEL LAUNCH PER STEP, issued back to back from C (g2048_step_n): what
+        `for k in range(K): step(actions[k])` does — every step reads and writes the boards in device memory —
+        without the interpreter between two launches (a Python loop issues a launch every ~6 us, a B200 steps
+        131,072 boards in ~3 us).  `actions`: contiguous uint8 [K,n] on the device (an open-loop sequence).
+        Returns (rewards f32 [K,n], dones bool [K,n]); `illegal`, `highest_exp`, `legal_mask_out` (uint8 [K,n])
+        are filled when given.  The env's running episode statistics (ep_score/ep_len/ep_return) are kept;
+        terminal boards and final_* of the intermediate steps are not reported (use step() for those)."""
+        n = self.num_envs
+        if self._step_counter is not None:
+            raise G2048Error("step_n is not available with a device-side step counter")
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device
+                and actions.is_contiguous() and actions.dim() == 2 and actions.shape[1] == n):
+            raise ValueError("actions must be a contiguous uint8 [K,%d] tensor on %s" % (n, self.device))
+        K = int(actions.shape[0])
+
+        def buf(t, dtype, what, alloc):
+            if t is None:
+                return torch.empty((K, n), dtype=dtype, device=self.device) if alloc else None
+            if not (isinstance(t, torch.Tensor) and t.dtype == dtype and t.device == self.device and t.is_contiguous()
+                    and tuple(t.shape) == (K, n)):
+                raise ValueError("%s must be a contiguous %s [%d,%d] tensor on %s" % (what, dtype, K, n, self.device))
+            return t
+        rewards = buf(rewards, torch.float32, "rewards", True)
+        dones_u8 = buf(dones, torch.uint8, "dones", True)
+        illegal = buf(illegal, torch.uint8, "illegal", False)
+        highest_exp = buf(highest_exp, torch.uint8, "highest_exp", False)
+        if legal_mask_out is None and self.legal_mask is not None and K:
+            legal_mask_out = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        legal_mask_out = buf(legal_mask_out, torch.uint8, "legal_mask_out", False)
+        if K == 0:
+            return rewards, dones_u8.view(torch.bool)
+        a = StepArgs(self._ptr(self.boards), self._ptr(actions), self._ptr(rewards), self._ptr(dones_u8),
+                     self._ptr(illegal), self._ptr(highest_exp), self._ptr(legal_mask_out), None,
+                     self._ptr(self.ep_score), self._ptr(self.ep_len), None, None, None, None,
+                     n, self.env_id_base, self.seed, self.step_index,
+                     self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0, None,
+                     self._ptr(self.ep_return), None)
+        self._launch(self.lib.g2048_step_n, C.byref(a), K, n)
+        self.step_index += K
+        if self.legal_mask is not None:
+            self.legal_mask.copy_(legal_mask_out[K - 1])
+        self.rewards.copy_(rewards[K - 1])
+        self._dones.copy_(dones_u8[K - 1])
+        return rewards, dones_u8.view(torch.bool)
+
+    def capture(self, fn, warmup=1):
+        """Capture `fn()` — any fixed sequence of step() / observe() / sample_actions-free policy work on this
+        env's device, e.g. `policy forward -> step` repeated T times — in a CUDA graph and return a callable
+        that replays it: one graph launch instead of one trip through the interpreter per kernel.  This is the
+        closed-loop answer to small batches (a 65,536-board step takes ~3 us on the GPU and ~4-6 us to issue
+        from Python); for open-loop action sequences step_n / step_many need no graph.
+
+        The env switches to its DEVICE-side step index (use_device_step_counter): the captured step kernels read
+        the index from device memory and advance it themselves, so every replay draws fresh tiles.  `fn` must
+        only touch tensors that stay alive and in place (write new actions INTO the tensors fn read);
+        `warmup` eager calls of fn run first (they are real steps).  Returns replay(); replay.graph is the
+        torch.cuda.CUDAGraph, replay.steps the number of env steps per replay."""
+        if self._step_counter is None:
+            self.use_device_step_counter(True)
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(int(warmup)):
+                fn()
+            before = self.step_index
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                fn()
+            steps = self.step_index - before
+            self.step_index = before            # capture does not execute
+        cur.wait_stream(side)
+
+        def replay():
+            graph.replay()
+            self.step_index += steps
+        replay.graph, replay.steps = graph, steps
+        return replay
 
     def step_many(self, actions=None, rewards=None, dones=None, illegal=None, boards_traj=None, policy=None,
                   n_steps=None, actions_out=None, legal_mask_out=None):
@@ -402,7 +488,7 @@ class BatchedGame2048:
         sd = dict(boards=self.boards.clone(), seed=self.seed, step_index=self.step_index,
                   reset_index=self.reset_index, env_id_base=self.env_id_base)
         if self.ep_score is not None:
-            sd.update(ep_score=self.ep_score.clone(), ep_len=self.ep_len.clone())
+            sd.update(ep_score=self.ep_score.clone(), ep_len=self.ep_len.clone(), ep_return=self.ep_return.clone())
         return sd
 
     def load_state_dict(self, sd):
@@ -414,6 +500,8 @@ class BatchedGame2048:
         if self.ep_score is not None and "ep_score" in sd:
             self.ep_score.copy_(sd["ep_score"])
             self.ep_len.copy_(sd["ep_len"])
+            if "ep_return" in sd:
+                self.ep_return.copy_(sd["ep_return"])
         if self.legal_mask is not None:
             self.status(legal_mask=self.legal_mask)
 
@@ -501,3 +589,79 @@ class HostSteppedEnv:
             self.close()
         except Exception:
             pass
+
+
+class StepSchedule:
+    """A pre-built list of step() calls, issued by ONE C call (g2048_step_list) instead of one trip through the
+    interpreter per launch.
+
+        sched = StepSchedule()
+        for j in range(K):
+            sched.add(games[j % len(games)], actions[j])       # any mix of BatchedGame2048 objects on ONE device
+        sched.run()                                            # K kernel launches, back to back
+
+    Each add() records a complete g2048_step call — the game's buffers, the action row and the step index that
+    call will have — and advances the game's host-side step index, exactly as game.step() would; run() launches
+    the recorded calls in order on the current stream.  A schedule is a one-shot object: the step indices are
+    baked in, so run() (or run(lo, hi) over consecutive slices) must be executed exactly once and in order.
+    Results land in each game's own output tensors (rewards, dones, ...), overwritten by that game's next step.
+    Use: many small vectorised envs stepped round-robin, or open-loop rollouts of small batches, where the GPU
+    finishes a step (~3 us for 131,072 boards) faster than Python can issue the next one (~6 us)."""
+
+    def __init__(self):
+        self._items = []
+        self._keep = []          # action tensors must outlive the launches
+        self._array = None
+        self._device = None
+        self._next = 0
+
+    def __len__(self):
+        return len(self._items)
+
+    def add(self, game, actions):
+        n = game.num_envs
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == game.device
+                and actions.is_contiguous() and actions.shape == (n,)):
+            raise ValueError("actions must be a contiguous uint8 [%d] tensor on %s" % (n, game.device))
+        if game._step_counter is not None:
+            raise G2048Error("StepSchedule needs the host-side step index (no device step counter)")
+        if self._device is None:
+            self._device = game.device
+        elif self._device != game.device:
+            raise ValueError("all games of a schedule must live on one device")
+        if self._array is not None:
+            raise G2048Error("the schedule was already built; make a new one")
+        game._build_step_args()
+        a = StepArgs.from_buffer_copy(game._args)
+        a.actions = actions.data_ptr()
+        a.step_index = game.step_index
+        a.boards = game.boards.data_ptr()
+        game.step_index += 1
+        self._items.append(a)
+        self._keep.append((game, actions))
+
+    def build(self):
+        if self._array is None:
+            arr = (StepArgs * len(self._items))(*self._items)
+            self._array, self._lib = arr, _lib.lib()
+        return self._array
+
+    def run(self, lo=None, hi=None):
+        """Launch items [lo, hi) (default: everything not yet launched) on the current stream."""
+        arr = self.build()
+        lo = self._next if lo is None else int(lo)
+        hi = len(self._items) if hi is None else int(hi)
+        if lo != self._next or hi < lo or hi > len(self._items):
+            raise G2048Error("a StepSchedule runs once, in order: next item is %d, got [%d, %d)" % (self._next, lo, hi))
+        if hi == lo:
+            return
+        idx = self._device.index
+        ptr = C.c_void_p(C.addressof(arr) + lo * C.sizeof(StepArgs))
+        if torch.cuda.current_device() == idx:
+            rc = self._lib.g2048_step_list(ptr, hi - lo, _raw_stream(idx))
+        else:
+            with torch.cuda.device(idx):
+                rc = self._lib.g2048_step_list(ptr, hi - lo, _raw_stream(idx))
+        self._next = hi
+        if rc:
+            check(rc)

@@ -48,6 +48,12 @@ int cuda_fail(cudaError_t e, const char* what) {
 #ifndef G2048_PREFETCH       // load the next iteration's board/action before computing this one
 #define G2048_PREFETCH 1
 #endif
+#ifndef G2048_PRE_PREFETCH   // L2-prefetch every thread's first board/action BEFORE griddepcontrol.wait (see the kernel)
+#define G2048_PRE_PREFETCH 1
+#endif
+#ifndef G2048_STAGGER        // ns between the start of consecutive warps of an SM sub-partition (0 = off)
+#define G2048_STAGGER 0
+#endif
 #ifndef G2048_PERSISTENT     // 1: grid-stride loop over a grid sized to the SM count; 0: one board per thread
 #define G2048_PERSISTENT 1
 #endif
@@ -146,6 +152,8 @@ struct StepParams {
   uint32_t* ep_len;
   uint32_t* final_score;
   uint32_t* final_len;
+  float* ep_return;
+  float* final_return;
   const uint4* forced_draws;
   uint64_t* step_counter;       // [0] step index, [1] CTA arrival ticket (0 between launches)
   uint32_t n;                   // < 2^32 - 256 (checked by the host)
@@ -170,8 +178,8 @@ constexpr PairLut make_pair_lut() {
 }
 __device__ const PairLut g_pair_lut = make_pair_lut();
 
-// Game2048Env.step (:76-100) for n boards.  EXTRAS=false is the lean variant used when
-// none of the optional outputs/inputs is requested (boards, actions, rewards, dones only).
+// Game2048Env.step (:76-100) for n boards.  OUT = 0 is the lean variant used when none of the
+// optional outputs/inputs is requested (boards, actions, rewards, dones only); see O_* below.
 // The 32 one-tile boards fresh_board() ORs together, built once per CTA in shared memory.
 __device__ __forceinline__ const Board4* make_reset_lut(Board4* s_lut) {
   if (threadIdx.x < 32) s_lut[threadIdx.x] = one_tile_board(threadIdx.x);
@@ -200,13 +208,30 @@ __device__ __forceinline__ uint4 load_board(const uint4* ptr) {
 #ifndef G2048_PAIR_LUT       // 1: the step kernel's reset path reads whole fresh boards from a 16 KB shared-memory
 #define G2048_PAIR_LUT 1     //    table (two_tile_board) instead of OR-ing two entries of the 32-entry one-tile table
 #endif
+// Optional outputs/inputs of a step as a COMPILE-TIME set (template parameter OUT of the step kernel): the output
+// sets the library's own callers use are kernels of their own — no pointer tests, no dead code, registers only for
+// what is written — and any other combination runs the O_GENERIC kernel, which tests every pointer at run time.
+//   0                                  lean: boards, actions, rewards, dones            (BASELINE configs 2, 3)
+//   O_MASK                             + legal mask                                     (BASELINE config 4)
+//   O_EPRUN                            + running episode score/length                   (g2048_env_step_host, `e2e`)
+//   O_ILLEGAL|O_HIGHEST|O_MASK         the evaluator (train.py:122-214)
+//   kOutAll                            everything SB3's Monitor + DummyVecEnv report    (Game2048VecEnv)
+constexpr uint32_t O_ILLEGAL = 1u, O_HIGHEST = 2u, O_MASK = 4u, O_TERMINAL = 8u, O_EPRUN = 16u, O_EPFINAL = 32u,
+                   O_EPRET = 64u, O_FORCED = 128u, O_GENERIC = 0x80000000u;
+constexpr uint32_t kOutEval = O_ILLEGAL | O_HIGHEST | O_MASK;
+constexpr uint32_t kOutAll = O_ILLEGAL | O_HIGHEST | O_MASK | O_TERMINAL | O_EPRUN | O_EPFINAL | O_EPRET;
+template <uint32_t OUT, uint32_t BIT> __device__ __forceinline__ bool has(const void* ptr) {
+  if constexpr ((OUT & O_GENERIC) != 0u) return ptr != nullptr;
+  else return (OUT & BIT) != 0u;
+}
+
 // The finishing half of board i (spawn, score, isend, auto-reset) and its stores; `m` is what the
 // move half (move_oriented) left.
-template <bool EXTRAS, bool COUNTER>
+template <uint32_t OUT, bool COUNTER>
 __device__ __forceinline__ void finish_and_store(const StepParams& p, const Board4* lut, uint32_t i, const Moved& m,
                                                  uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
   Words w;
-  if (EXTRAS && p.forced_draws) {
+  if (has<OUT, O_FORCED>(p.forced_draws)) {
     const uint4 f = p.forced_draws[i];
     w = Words{f.x, f.y, f.z, f.w};
   } else if (COUNTER) {
@@ -215,34 +240,42 @@ __device__ __forceinline__ void finish_and_store(const StepParams& p, const Boar
     w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.keys));
   }
   uint4 bd;
-  const StepOut o = finish_step<(G2048_PAIR_LUT && !G2048_TMA)>(lut, m, w, p.max_tile_exp, EXTRAS && p.highest_exp != nullptr,
+  const StepOut o = finish_step<(G2048_PAIR_LUT && !G2048_TMA)>(lut, m, w, p.max_tile_exp, has<OUT, O_HIGHEST>(p.highest_exp),
                                                     auto_reset, bd.x, bd.y, bd.z, bd.w);
+  const float reward = o.legal ? o.score : p.illegal_move_reward;                        // :90 / :95
   p.boards_out[i] = bd;
-  p.rewards[i] = o.legal ? o.score : p.illegal_move_reward;          // :90 / :95
+  p.rewards[i] = reward;
   p.dones[i] = o.done ? 1 : 0;
-  if (EXTRAS) {
-    if (p.illegal) p.illegal[i] = o.legal ? 0 : 1;                   // :82, :93
-    if (p.highest_exp) p.highest_exp[i] = (uint8_t)o.highest;        // :97
+  if constexpr (OUT != 0u) {
+    if (has<OUT, O_ILLEGAL>(p.illegal)) p.illegal[i] = o.legal ? 0 : 1;                  // :82, :93
+    if (has<OUT, O_HIGHEST>(p.highest_exp)) p.highest_exp[i] = (uint8_t)o.highest;       // :97
+    // (in a specialised kernel a group bit stands for all pointers of the group; the generic one tests each)
+    const bool h_es = has<OUT, O_EPRUN>(p.ep_score), h_el = has<OUT, O_EPRUN>(p.ep_len);
+    const bool h_er = has<OUT, O_EPRET>(p.ep_return);
     uint32_t es = 0, el = 0;
-    if (p.ep_score) es = p.ep_score[i] + (uint32_t)o.score;          // :86
-    if (p.ep_len) el = p.ep_len[i] + 1u;
+    float er = 0.f;
+    if (h_es) es = p.ep_score[i] + (uint32_t)o.score;                                    // :86
+    if (h_el) el = p.ep_len[i] + 1u;
+    if (h_er) er = p.ep_return[i] + reward;              // what SB3's Monitor sums: the rewards the agent saw
     if (o.done) {
-      if (p.terminal_boards) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
-      if (p.final_score) p.final_score[i] = es;
-      if (p.final_len) p.final_len[i] = el;
-      if (auto_reset) es = el = 0u;
+      if (has<OUT, O_TERMINAL>(p.terminal_boards)) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
+      if (has<OUT, O_EPFINAL>(p.final_score)) p.final_score[i] = es;
+      if (has<OUT, O_EPFINAL>(p.final_len)) p.final_len[i] = el;
+      if (has<OUT, O_EPRET>(p.final_return)) p.final_return[i] = er;
+      if (auto_reset) { es = el = 0u; er = 0.f; }
     }
-    if (p.ep_score) p.ep_score[i] = es;
-    if (p.ep_len) p.ep_len[i] = el;
-    if (p.legal_mask) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
+    if (h_es) p.ep_score[i] = es;
+    if (h_el) p.ep_len[i] = el;
+    if (h_er) p.ep_return[i] = er;
+    if (has<OUT, O_MASK>(p.legal_mask)) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
   }
 }
 
-template <bool EXTRAS, bool COUNTER>
+template <uint32_t OUT, bool COUNTER>
 __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
                                                uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
                                                uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
-  finish_and_store<EXTRAS, COUNTER>(p, lut, i, move_oriented(a, b, c, d, so), dev_key, dev_idx_lo, auto_reset);
+  finish_and_store<OUT, COUNTER>(p, lut, i, move_oriented(a, b, c, d, so), dev_key, dev_idx_lo, auto_reset);
 }
 
 #ifndef G2048_PIPELINE       // 1: software-pipelined loop — the move half of board j+1 and the finishing half of
@@ -290,7 +323,7 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool EXTRAS, bool COUNTER>
+template <uint32_t OUT, bool COUNTER>
 __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kernel(const StepParams p) {
 #if G2048_PAIR_LUT && !G2048_TMA
   __shared__ alignas(128) Board4 s_lut[1024];
@@ -336,6 +369,16 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
 #if !G2048_TMA
   const uint32_t stride = gridDim.x * blockDim.x;               // the CTA width is chosen at launch (shape_for)
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+#endif
+#if G2048_PRE_PREFETCH && !G2048_TMA
+  // Cold start: after griddepcontrol.wait every warp's first board is an HBM round trip (~1 us of a ~12 us launch)
+  // with nothing to compute meanwhile.  An L2 prefetch has no architectural effect (the L2 is the point of
+  // coherence: a line the previous launch is still writing is simply already there), so the first lines can be
+  // requested while the previous launch drains: one lane per 128-byte line (8 boards), one per warp for the actions.
+  if (i < n) {
+    if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.boards + i));
+    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + i));
+  }
 #endif
 #if G2048_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -408,7 +451,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     uint32_t a, b, c, d;
     orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
     const Sel4 so = s_sel[4u + act];
-    if (valid) step_and_store<EXTRAS, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
+    if (valid) step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
     if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
     if (++fill_stage == (uint32_t)kStages) { fill_stage = 0; fill_parity ^= 1u; }
   }
@@ -442,18 +485,24 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
       const Sel4 so = s_sel[4u + act];
       if (more_next) { bd = load_board(p.boards + i_next); action = p.actions[i_next]; }
       const Moved m_next = move_oriented(a, b, c, d, so);
-      finish_and_store<EXTRAS, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
+      finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
       m = m_next;
       i = i_cur;
       more = more_next;
     }
-    finish_and_store<EXTRAS, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
+    finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
   }
 #else
   const uint4* pb = p.boards + i;
   const uint8_t* pa = p.actions + i;
   uint4 bd = load_board(pb);
   uint32_t action = *pa;
+#if G2048_STAGGER
+  // Experiment: the eight warps of an SM sub-partition run the same instruction stream in near lockstep — all in
+  // the ALU-heavy move, then all in the FMA-heavy Philox/spawn — so the two pipes take turns idling.  Start them
+  // G2048_STAGGER ns apart (their first loads are in flight meanwhile).
+  __nanosleep((threadIdx.x >> 7) * G2048_STAGGER);
+#endif
   while (true) {
     const uint32_t i_next = i + stride;
     const bool more = G2048_PERSISTENT && i_next < n && i_next > i;
@@ -476,7 +525,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
 #endif
     }
 #endif
-    step_and_store<EXTRAS, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
+    step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
     if (!more) break;
 #if !G2048_PREFETCH
     bd = load_board(p.boards + i_next); action = p.actions[i_next];
@@ -788,6 +837,115 @@ g2048_draw_words_kernel(uint4* out, uint64_t n, uint64_t env_id_base, uint64_t s
   }
 }
 
+// ------------------------------------------------------------------------------------
+// One env, one launch (g2048_one): the single-env class of the reference (Game2048Env.step/reset/move/add_tile/
+// isend/highest/stack on ONE 4x4 Matrix of tile values) as a single kernel over a packed in/out block.  The block
+// may live in pinned host memory (the device reads and writes it over PCIe: zero copy), so a call is one launch
+// and one stream synchronisation — the per-call latency floor for train.py:150-165 / gather_training_data.py
+// :141-145, which step one env at a time.
+// ------------------------------------------------------------------------------------
+struct OneParams {
+  G2048OneIO* io;
+  int op;
+  uint32_t action;
+  uint32_t trial;
+  uint64_t seed, index;
+  float illegal_move_reward;
+  uint32_t max_tile_exp;
+};
+
+__global__ void __launch_bounds__(256) g2048_one_kernel(const OneParams p) {
+  __shared__ long long s_vals[16];
+  __shared__ Board4 s_lut[32];
+  const Board4* lut = make_reset_lut(s_lut);
+  G2048OneIO* io = p.io;
+  if (threadIdx.x == 0) {
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    uint32_t bad = 0u;
+    long long vals[16];
+    for (int c = 0; c < 16; ++c) {
+      const long long v = p.op == G2048_ONE_RESET ? 0ll : (long long)io->values[c];
+      vals[c] = v;
+      uint32_t e = 0u;
+      if (v != 0) {
+        if (v >= 2 && v <= (1ll << 31) && (v & (v - 1)) == 0) e = 63u - (uint32_t)__clzll(v);
+        else ++bad;
+      }
+      r[c >> 2] |= e << (8 * (c & 3));
+    }
+    float reward = 0.f;
+    uint32_t score = 0u, done = 0u, illegal = 0u, changed = 0u;
+    bool write = false;
+    if (bad == 0u || p.op == G2048_ONE_RESET) {
+      switch (p.op) {
+        case G2048_ONE_STEP: {                                                           // :76-100, no auto-reset
+          const Words w = draw_words(p.seed, 0ull, p.index, TAG_STEP);
+          const StepOut o = step_board(lut, r[0], r[1], r[2], r[3], p.action & 3u, w, p.max_tile_exp, true, false);
+          score = (uint32_t)o.score;
+          reward = o.legal ? o.score : p.illegal_move_reward;
+          done = o.done ? 1u : 0u;
+          illegal = o.legal ? 0u : 1u;
+          changed = o.legal ? 1u : 0u;
+          write = o.legal;
+          break;
+        }
+        case G2048_ONE_RESET: {                                                          // :102-111
+          const Words w = draw_words(p.seed, 0ull, p.index, TAG_RESET);
+          fresh_board(lut, w.w1, w.w2, r[0], r[1], r[2], r[3]);
+          write = true;
+          break;
+        }
+        case G2048_ONE_MOVE: {                                                           // :194-241
+          const uint32_t act = p.action & 3u;
+          uint32_t a, b, c, d, m0, m1, m2, m3;
+          orient(kOrientIn[act], r[0], r[1], r[2], r[3], a, b, c, d);
+          const uint32_t a0 = a, b0 = b, c0 = c, d0 = d;
+          score = (uint32_t)slide_merge(a, b, c, d);
+          reward = (float)score;
+          changed = ((((a ^ a0) | (b ^ b0)) | ((c ^ c0) | (d ^ d0))) != 0u) ? 1u : 0u;
+          orient(kOrientOut[act], a, b, c, d, m0, m1, m2, m3);
+          if (changed && !p.trial) { r[0] = m0; r[1] = m1; r[2] = m2; r[3] = m3; write = true; }
+          break;
+        }
+        case G2048_ONE_ADD_TILE: {                                                       // :166-176
+          const Words w = draw_words(p.seed, 0ull, p.index, TAG_STEP);
+          changed = spawn(r[0], r[1], r[2], r[3], w.w0) != 0u ? 1u : 0u;
+          write = changed != 0u;
+          break;
+        }
+        default: break;                                                                  // G2048_ONE_STATUS: queries only
+      }
+    }
+    if (write) {
+      for (int c = 0; c < 16; ++c) {
+        const uint32_t e = (r[c >> 2] >> (8 * (c & 3))) & 0xFFu;
+        vals[c] = e ? (long long)(1ull << (e & 63u)) : 0ll;
+        io->values[c] = vals[c];
+      }
+    }
+    for (int c = 0; c < 16; ++c) s_vals[c] = vals[c];
+    const uint32_t h = highest_exp(r[0], r[1], r[2], r[3]);
+    const uint32_t empties = count_empty(r[0], r[1], r[2], r[3]);
+    io->reward = reward;
+    io->score = score;
+    io->done = (uint8_t)done;
+    io->illegal = (uint8_t)illegal;
+    io->changed = (uint8_t)changed;
+    io->highest_exp = (uint8_t)h;                                                        // :190-192
+    io->legal_mask = (uint8_t)legal_mask(r[0], r[1], r[2], r[3]);
+    io->n_empty = (uint8_t)empties;                                                      // :186-188
+    io->is_end = ((p.max_tile_exp != 0u && h == p.max_tile_exp) ||                         // :262-280
+                  (empties == 0u && full_board_is_dead(r[0], r[1], r[2], r[3]))) ? 1 : 0;
+    io->bad_cells = (uint8_t)(bad > 255u ? 255u : bad);
+  }
+  __syncthreads();
+  // stack() (:17-32) of the Matrix as it is now, straight from the tile VALUES: channel 0 = empty, channel k =
+  // (cell == 2^k); a cell holding anything else lights no channel, exactly like the reference's comparison.
+  const uint32_t ch = threadIdx.x >> 4, cell = threadIdx.x & 15u;
+  const long long v = s_vals[cell];
+  io->obs[threadIdx.x] = (ch == 0u) ? (v == 0 ? 1 : 0) : (v == (1ll << ch) ? 1 : 0);
+}
+
 int launch_check(const char* name) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, name);
@@ -831,14 +989,59 @@ static G2048StepArgs slice_args(const G2048StepArgs& a, uint64_t lo, uint64_t m)
   adv(s.boards, 16); adv(s.boards_out, 16); adv(s.actions, 1); adv(s.rewards, 1); adv(s.dones, 1);
   adv(s.illegal, 1); adv(s.highest_exp, 1); adv(s.legal_mask, 1); adv(s.terminal_boards, 16);
   adv(s.ep_score, 1); adv(s.ep_len, 1); adv(s.final_score, 1); adv(s.final_len, 1); adv(s.forced_draws, 4);
+  adv(s.ep_return, 1); adv(s.final_return, 1);
   s.n = m;
   s.env_id_base = a.env_id_base + lo;
   return s;
 }
 
-// One launch; the env ids of the call do not cross a multiple of 2^32.
-static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter) {
-  StepParams p;
+// The step kernels the library instantiates: (output set, device-side step counter) -> kernel.  Any other
+// combination of optional pointers runs the generic kernel.
+struct StepKernelEntry { uint32_t out; bool counter; const void* fn; };
+static const StepKernelEntry kStepKernels[] = {
+    {0u, false, (const void*)g2048_step_kernel<0u, false>},
+    {0u, true, (const void*)g2048_step_kernel<0u, true>},
+    {O_MASK, false, (const void*)g2048_step_kernel<O_MASK, false>},
+    {O_MASK, true, (const void*)g2048_step_kernel<O_MASK, true>},
+    {O_EPRUN, false, (const void*)g2048_step_kernel<O_EPRUN, false>},
+    {kOutEval, false, (const void*)g2048_step_kernel<kOutEval, false>},
+    {kOutAll, false, (const void*)g2048_step_kernel<kOutAll, false>},
+    {O_GENERIC, false, (const void*)g2048_step_kernel<O_GENERIC, false>},
+    {O_GENERIC, true, (const void*)g2048_step_kernel<O_GENERIC, true>},
+};
+// The optional pointers of a call as an output set; *exact = false when a pointer group is only partly given
+// (the specialised kernels write whole groups).
+static uint32_t output_set(const G2048StepArgs* a, bool* exact) {
+  uint32_t have = 0u;
+  *exact = true;
+  if (a->illegal) have |= O_ILLEGAL;
+  if (a->highest_exp) have |= O_HIGHEST;
+  if (a->legal_mask) have |= O_MASK;
+  if (a->terminal_boards) have |= O_TERMINAL;
+  if (a->forced_draws) have |= O_FORCED;
+  auto group = [&](const void* x, const void* y, uint32_t bit) {
+    if (x && y) have |= bit;
+    else if (x || y) { have |= bit; *exact = false; }
+  };
+  group(a->ep_score, a->ep_len, O_EPRUN);
+  group(a->final_score, a->final_len, O_EPFINAL);
+  group(a->ep_return, a->final_return, O_EPRET);
+  return have;
+}
+static const void* pick_step_kernel(const G2048StepArgs* a) {
+  bool exact = true;
+  const uint32_t have = output_set(a, &exact);
+  const bool counter = a->step_counter != nullptr;
+  const void* generic = nullptr;
+  for (const StepKernelEntry& e : kStepKernels) {
+    if (e.counter != counter) continue;
+    if (exact && e.out == have) return e.fn;
+    if (e.out == O_GENERIC) generic = e.fn;
+  }
+  return generic;
+}
+
+static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepParams& p) {
   p.boards = reinterpret_cast<const uint4*>(a->boards);
   p.boards_out = reinterpret_cast<uint4*>(a->boards_out ? a->boards_out : a->boards);
   p.actions = a->actions;
@@ -852,6 +1055,8 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   p.ep_len = a->ep_len;
   p.final_score = a->final_score;
   p.final_len = a->final_len;
+  p.ep_return = a->ep_return;
+  p.final_return = a->final_return;
   p.forced_draws = reinterpret_cast<const uint4*>(a->forced_draws);
   p.step_counter = a->step_counter;
   p.n = (uint32_t)a->n;
@@ -862,93 +1067,146 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = (a->flags & ~kFlagBumpCounter) | (bump_counter ? kFlagBumpCounter : 0u);
-  const bool extras = a->illegal || a->highest_exp || a->legal_mask || a->terminal_boards || a->ep_score ||
-                      a->ep_len || a->final_score || a->final_len || a->forced_draws;
-  cudaLaunchConfig_t cfg;
+}
+
+// Launch configuration of a step over n boards (shape_for), with the kernel attributes it relies on set once per
+// device and host thread.
+static void step_launch_config(uint64_t n, cudaStream_t s, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
   std::memset(&cfg, 0, sizeof cfg);
 #if G2048_TMA || !G2048_PAIR_LUT
   {
-    const uint64_t need = (a->n + kStepThreads - 1) / kStepThreads, cap = (uint64_t)sm_count() * kStepCtasPerSm;
+    const uint64_t need = (n + kStepThreads - 1) / kStepThreads, cap = (uint64_t)sm_count() * kStepCtasPerSm;
     cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
   }
   cfg.blockDim = dim3(kStepThreads);
 #elif G2048_PERSISTENT
-  const LaunchShape shape = shape_for(a->n, sizeof(PairLut) + 256);
+  const LaunchShape shape = shape_for(n, sizeof(PairLut) + 256);
   cfg.gridDim = dim3(shape.grid);
   cfg.blockDim = dim3(shape.block);
   cfg.dynamicSmemBytes = shape.pad_smem;
-  {
-    static thread_local uint64_t seen = 0;
-    if (first_use_on_current_device(seen)) {                       // once per device and thread: allow the padding, prefer shared memory
-      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
-      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
-      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
-      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
-      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    }
-  }
 #else
-  cfg.gridDim = dim3((unsigned)((a->n + kStepThreads - 1) / kStepThreads));
+  cfg.gridDim = dim3((unsigned)((n + kStepThreads - 1) / kStepThreads));
   cfg.blockDim = dim3(kStepThreads);
 #endif
+  {
+    static thread_local uint64_t seen = 0;
+    if (first_use_on_current_device(seen)) {           // once per device and thread: allow the padding, prefer shared memory
+      for (const StepKernelEntry& e : kStepKernels) {
+#if G2048_TMA
+        cudaFuncSetAttribute(e.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 50);   // a ring per CTA, two CTAs per SM
+#else
+        cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
+        cudaFuncSetAttribute(e.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#endif
+      }
+    }
+  }
   cfg.stream = s;
 #if G2048_PDL
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#else
+  (void)attr;
 #endif
-#if G2048_TMA
-  // The staged kernel keeps a shared-memory ring per CTA: ask for a carveout that fits kCtasPerSm of them.
-  {
-    static thread_local uint64_t seen = 0;
-    if (first_use_on_current_device(seen)) {
-      const int pct = 50;
-      cudaFuncSetAttribute(g2048_step_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      cudaFuncSetAttribute(g2048_step_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      cudaFuncSetAttribute(g2048_step_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      cudaFuncSetAttribute(g2048_step_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
-  }
-#endif
-  const bool counter = a->step_counter != nullptr;
-  const cudaError_t le =
-      extras ? (counter ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<true, true>, p)
-                        : cudaLaunchKernelEx(&cfg, g2048_step_kernel<true, false>, p))
-             : (counter ? cudaLaunchKernelEx(&cfg, g2048_step_kernel<false, true>, p)
-                        : cudaLaunchKernelEx(&cfg, g2048_step_kernel<false, false>, p));
+}
+
+// One launch; the env ids of the call do not cross a multiple of 2^32.
+static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter) {
+  StepParams p;
+  fill_step_params(a, bump_counter, p);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  step_launch_config(a->n, s, cfg, attr);
+  void* kargs[] = {&p};
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, pick_step_kernel(a), kargs);
   if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_kernel)");
   return G2048_OK;
 }
 
-int g2048_step(const G2048StepArgs* a, void* stream) {
-  if (!a) return fail(G2048_ERR_INVALID, "g2048_step: args is NULL");
+static int check_step_args(const G2048StepArgs* a, const char* fn) {
+  if (!a) return fail(G2048_ERR_INVALID, "%s: args is NULL", fn);
   if (a->n == 0) return G2048_OK;
   if (!a->boards || !a->actions || !a->rewards || !a->dones)
-    return fail(G2048_ERR_INVALID, "g2048_step: boards, actions, rewards and dones are required");
+    return fail(G2048_ERR_INVALID, "%s: boards, actions, rewards and dones are required", fn);
   if (!aligned16(a->boards) || !aligned16(a->boards_out) || !aligned16(a->terminal_boards) ||
       !aligned16(a->forced_draws))
-    return fail(G2048_ERR_ALIGN,
-                "g2048_step: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned");
-  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_step: max_tile_exp %u > 63", a->max_tile_exp);
+    return fail(G2048_ERR_ALIGN, "%s: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned", fn);
+  if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "%s: max_tile_exp %u > 63", fn, a->max_tile_exp);
   if (a->flags & ~G2048_FLAG_AUTO_RESET)
-    return fail(G2048_ERR_INVALID, "g2048_step: unknown flags 0x%x (the policy flags belong to g2048_step_many)", a->flags);
-  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "g2048_step: n must be < 2^32 - 256 per call");
-  const cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // The kernel treats the high half of the env id as launch-uniform (Philox head): a call whose
-  // ids cross a multiple of 2^32 is issued as two launches.
+    return fail(G2048_ERR_INVALID, "%s: unknown flags 0x%x (the policy flags belong to g2048_step_many)", fn, a->flags);
+  if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "%s: n must be < 2^32 - 256 per call", fn);
+  return G2048_OK;
+}
+
+// One validated step.  The kernel treats the high half of the env id as launch-uniform (Philox head): a call whose
+// ids cross a multiple of 2^32 is issued as two launches.
+static int issue_step(const G2048StepArgs* a, cudaStream_t s) {
   const uint64_t to_boundary = 0x100000000ull - (a->env_id_base & 0xFFFFFFFFull);
   if (a->n > to_boundary) {
     const G2048StepArgs first = slice_args(*a, 0, to_boundary), second = slice_args(*a, to_boundary, a->n - to_boundary);
-    int rc = launch_step(&first, s, false);
-    if (rc == G2048_OK) rc = launch_step(&second, s, true);      // both read the index, the second advances it
+    const int rc = launch_step(&first, s, false);
+    return rc == G2048_OK ? launch_step(&second, s, true) : rc;     // both read the index, the second advances it
+  }
+  return launch_step(a, s, true);
+}
+
+int g2048_step(const G2048StepArgs* a, void* stream) {
+  const int bad = check_step_args(a, "g2048_step");
+  if (bad || a->n == 0) return bad;
+  const int rc = issue_step(a, static_cast<cudaStream_t>(stream));
+  if (rc != G2048_OK) return rc;
+  return launch_check("g2048_step_kernel");
+}
+
+// n_steps steps, one kernel launch per step, issued back to back from C: the per-launch host cost is one
+// cudaLaunchKernelEx (~2 us) instead of a trip through the caller's interpreter (4-6 us per step from Python), which
+// is what bounds a batch that a GPU steps in ~3 us (BASELINE config 3 sharded over 8 GPUs: 131,072 boards each).
+int g2048_step_n(const G2048StepArgs* a, uint32_t n_steps, uint64_t row_stride, void* stream) {
+  const int bad = check_step_args(a, "g2048_step_n");
+  if (bad || a->n == 0 || n_steps == 0) return bad;
+  if (a->step_counter) return fail(G2048_ERR_INVALID, "g2048_step_n: step_counter must be NULL (the step index is advanced on the host)");
+  if (a->boards_out) return fail(G2048_ERR_INVALID, "g2048_step_n: boards_out must be NULL (the steps run in place)");
+  if (row_stride != 0 && row_stride < a->n) return fail(G2048_ERR_INVALID, "g2048_step_n: row_stride must be 0 or >= n");
+  if (!aligned16(a->terminal_boards ? a->terminal_boards + 16 * row_stride : nullptr))
+    return fail(G2048_ERR_ALIGN, "g2048_step_n: terminal_boards rows must stay 16-byte aligned");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  G2048StepArgs k = *a;
+  for (uint32_t t = 0; t < n_steps; ++t) {
+    const int rc = issue_step(&k, s);
     if (rc != G2048_OK) return rc;
-  } else {
-    const int rc = launch_step(a, s, true);
+    // per-step arrays move on by one row; per-env state (boards, running episode statistics) stays
+    k.actions += row_stride; k.rewards += row_stride; k.dones += row_stride;
+    if (k.illegal) k.illegal += row_stride;
+    if (k.highest_exp) k.highest_exp += row_stride;
+    if (k.legal_mask) k.legal_mask += row_stride;
+    if (k.terminal_boards) k.terminal_boards += 16 * row_stride;
+    if (k.final_score) k.final_score += row_stride;
+    if (k.final_len) k.final_len += row_stride;
+    if (k.final_return) k.final_return += row_stride;
+    if (k.forced_draws) k.forced_draws += 4 * row_stride;
+    k.step_index += 1;
+  }
+  return launch_check("g2048_step_kernel");
+}
+
+// A caller-built list of steps, issued by one call: element j is a complete g2048_step call (its own boards, rows,
+// step index ...), launched in order on `stream`.  The elements may belong to different env sets.
+int g2048_step_list(const G2048StepArgs* list, uint64_t count, void* stream) {
+  if (count == 0) return G2048_OK;
+  if (!list) return fail(G2048_ERR_INVALID, "g2048_step_list: list is NULL");
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (uint64_t j = 0; j < count; ++j) {
+    const G2048StepArgs* a = list + j;
+    const int bad = check_step_args(a, "g2048_step_list");
+    if (bad) {
+      char first[sizeof g_err];
+      std::snprintf(first, sizeof first, "%s", g_err);
+      return fail(bad, "g2048_step_list: element %llu: %s", (unsigned long long)j, first);
+    }
+    if (a->n == 0) continue;
+    const int rc = issue_step(a, s);
     if (rc != G2048_OK) return rc;
   }
   return launch_check("g2048_step_kernel");
@@ -1165,6 +1423,29 @@ int g2048_draw_words(uint32_t* words, uint64_t n, uint64_t env_id_base, uint64_t
   g2048_draw_words_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<uint4*>(words), n, env_id_base, seed, index, tag);
   return launch_check("g2048_draw_words_kernel");
+}
+
+int g2048_one(G2048OneIO* io, int op, int action, int trial, uint64_t seed, uint64_t index,
+              float illegal_move_reward, uint32_t max_tile_exp, void* stream, int synchronize) {
+  if (!io) return fail(G2048_ERR_INVALID, "g2048_one: io is NULL");
+  if (reinterpret_cast<uintptr_t>(io) & 7u) return fail(G2048_ERR_ALIGN, "g2048_one: io must be 8-byte aligned");
+  if (op < G2048_ONE_STEP || op > G2048_ONE_STATUS) return fail(G2048_ERR_INVALID, "g2048_one: unknown op %d", op);
+  if (max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_one: max_tile_exp %u > 63", max_tile_exp);
+  OneParams p;
+  p.io = io;
+  p.op = op;
+  p.action = (uint32_t)action;
+  p.trial = trial ? 1u : 0u;
+  p.seed = seed;
+  p.index = index;
+  p.illegal_move_reward = illegal_move_reward;
+  p.max_tile_exp = max_tile_exp;
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  g2048_one_kernel<<<1, 256, 0, s>>>(p);
+  const int rc = launch_check("g2048_one_kernel");
+  if (rc != G2048_OK) return rc;
+  if (synchronize) G2048_CUDA(cudaStreamSynchronize(s));
+  return G2048_OK;
 }
 
 // ---- stateful host-buffer API ---------------------------------------------------------

@@ -333,18 +333,53 @@ G2048_DEV float slide_merge(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) 
 // Returns n_empty BEFORE the spawn (0 => nothing placed).
 // `enable` = 0xFFFFFFFF to place the tile, 0 to leave the board untouched (illegal move:
 // no tile, :91-95).
+//
+// Build-time flavours (scripts/kernel_variants.py; all bit-identical):
+//   G2048_SPAWN_ALU    1: the spawn's adds and constant shifts as IADD3 / SHF (ALU pipe) instead of IMAD /
+//                         IMAD.HI: the spawn follows the Philox rounds in the instruction stream and is the
+//                         FMA-heavy stretch of the step, while the move before it is the ALU-heavy one
+//   G2048_MADHI_PAIR   1: the tile insertion hi32(t * m) + r as ONE wide multiply-add whose 64-bit addend is the
+//                         register pair {t, r} — mad.hi's addend {0, r} costs a register zeroing per row; the
+//                         low half of t * m is 0 for every t, m used here, so any low addend word is harmless
+#ifndef G2048_SPAWN_ALU
+#define G2048_SPAWN_ALU 0
+#endif
+#ifndef G2048_MADHI_PAIR
+#define G2048_MADHI_PAIR 0
+#endif
+#ifdef G2048_HOST_SIM
+inline uint32_t sp_add(uint32_t x, uint32_t y) { return x + y; }
+template <int S> inline uint32_t sp_shr(uint32_t x) { return x >> S; }
+inline uint32_t insert_tile(uint32_t t, uint32_t mult, uint32_t r) { return madhi(t, mult, r); }
+#else
+__device__ __forceinline__ uint32_t sp_add(uint32_t x, uint32_t y) { return G2048_SPAWN_ALU ? (x + y) : addf(x, y); }
+template <int S> __device__ __forceinline__ uint32_t sp_shr(uint32_t x) { return G2048_SPAWN_ALU ? (x >> S) : shr<S>(x); }
+__device__ __forceinline__ uint32_t insert_tile(uint32_t t, uint32_t mult, uint32_t r) {
+#if G2048_MADHI_PAIR
+  uint32_t d;
+  asm("{\n\t.reg .b64 c, p;\n\t.reg .b32 lo;\n\t"
+      "mov.b64 c, {%1, %3};\n\t"
+      "mad.wide.u32 p, %1, %2, c;\n\t"
+      "mov.b64 {lo, %0}, p;\n\t}"
+      : "=r"(d) : "r"(t), "r"(mult), "r"(r));
+  return d;
+#else
+  return madhi(t, mult, r);
+#endif
+}
+#endif
 G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t w,
                          uint32_t enable = 0xFFFFFFFFu) {
   // e_i: bit 7 set where the cell is empty; q_i: 0/1 per byte
-  const uint32_t e0 = ~addf(r0, L7) & H, e1 = ~addf(r1, L7) & H, e2 = ~addf(r2, L7) & H, e3 = ~addf(r3, L7) & H;
-  const uint32_t q0 = shr<7>(e0), q1 = shr<7>(e1), q2 = shr<7>(e2), q3 = shr<7>(e3);
+  const uint32_t e0 = ~sp_add(r0, L7) & H, e1 = ~sp_add(r1, L7) & H, e2 = ~sp_add(r2, L7) & H, e3 = ~sp_add(r3, L7) & H;
+  const uint32_t q0 = sp_shr<7>(e0), q1 = sp_shr<7>(e1), q2 = sp_shr<7>(e2), q3 = sp_shr<7>(e3);
   // inclusive row-major prefix counts of empties, one per byte (<= 16: no carries);
   // byte 3 of each word is the running total, broadcast into the next row's offset
   const uint32_t p0 = q0 * K1;
   const uint32_t p1 = q1 * K1 + prmt(p0, 0u, 0x3333u);
   const uint32_t p2 = q2 * K1 + prmt(p1, 0u, 0x3333u);
   const uint32_t p3 = q3 * K1 + prmt(p2, 0u, 0x3333u);
-  const uint32_t n = shr<24>(p3);
+  const uint32_t n = sp_shr<24>(p3);
   const uint32_t k = __umulhi(w, n);
   const uint32_t f = w * n;
   // target = the cell with prefix == k+1 that is empty:  (p > k) and not (p > k+1)
@@ -356,16 +391,16 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
   // zero multiplier (illegal move: no tile, :91-95) disables the spawn.
 #if defined(G2048_SPREAD_INSERT) && G2048_SPREAD_INSERT
   const uint32_t tile = ((f < P2_THRESHOLD) ? K1 : 2u * K1) & enable;                             // :168
-  r0 |= spread(addf(p0, gk) & ~addf(p0, gk1) & e0) & tile;
-  r1 |= spread(addf(p1, gk) & ~addf(p1, gk1) & e1) & tile;
-  r2 |= spread(addf(p2, gk) & ~addf(p2, gk1) & e2) & tile;
-  r3 |= spread(addf(p3, gk) & ~addf(p3, gk1) & e3) & tile;
+  r0 |= spread(sp_add(p0, gk) & ~sp_add(p0, gk1) & e0) & tile;
+  r1 |= spread(sp_add(p1, gk) & ~sp_add(p1, gk1) & e1) & tile;
+  r2 |= spread(sp_add(p2, gk) & ~sp_add(p2, gk1) & e2) & tile;
+  r3 |= spread(sp_add(p3, gk) & ~sp_add(p3, gk1) & e3) & tile;
 #else
   const uint32_t mult = ((f < P2_THRESHOLD) ? (1u << 25) : (1u << 26)) & enable;                  // :168
-  r0 = madhi(addf(p0, gk) & ~addf(p0, gk1) & e0, mult, r0);
-  r1 = madhi(addf(p1, gk) & ~addf(p1, gk1) & e1, mult, r1);
-  r2 = madhi(addf(p2, gk) & ~addf(p2, gk1) & e2, mult, r2);
-  r3 = madhi(addf(p3, gk) & ~addf(p3, gk1) & e3, mult, r3);
+  r0 = insert_tile(sp_add(p0, gk) & ~sp_add(p0, gk1) & e0, mult, r0);
+  r1 = insert_tile(sp_add(p1, gk) & ~sp_add(p1, gk1) & e1, mult, r1);
+  r2 = insert_tile(sp_add(p2, gk) & ~sp_add(p2, gk1) & e2, mult, r2);
+  r3 = insert_tile(sp_add(p3, gk) & ~sp_add(p3, gk1) & e3, mult, r3);
 #endif
   return n;
 }
@@ -448,7 +483,7 @@ G2048_DEV uint32_t legal_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3
   const uint32_t up = (~n0 & n1) | (~n1 & n2) | (~n2 & n3) | eqv;     // hole above a tile
   const uint32_t dn = (n0 & ~n1) | (n1 & ~n2) | (n2 & ~n3) | eqv;     // hole below a tile
   // horizontal pairs: byte j of s_i is cell (i, j+1); only byte lanes 0..2 are pairs
-  const uint32_t s0 = r0 >> 8, s1 = r1 >> 8, s2 = r2 >> 8, s3 = r3 >> 8;
+  const uint32_t s0 = shr<8>(r0), s1 = shr<8>(r1), s2 = shr<8>(r2), s3 = shr<8>(r3);
   const uint32_t m0 = addf(s0, L7), m1 = addf(s1, L7), m2 = addf(s2, L7), m3 = addf(s3, L7);
   const uint32_t eqh = (~addf(r0 ^ s0, L7) & n0) | (~addf(r1 ^ s1, L7) & n1) |
                        (~addf(r2 ^ s2, L7) & n2) | (~addf(r3 ^ s3, L7) & n3);

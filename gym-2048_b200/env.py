@@ -4,8 +4,8 @@ Same constructor, attributes, method names, argument meaning and error behaviour
 `/root/reference/env/envs/game2048_env.py` (class :34-288, `stack` :17-32, `IllegalMove`
 :14-15) so the reference's callers (train.py:150-165,183-184; gather_training_data.py
 :91,141-145,191; env/envs/test_game2048_env.py) run unchanged.  Every game rule is evaluated
-by the CUDA kernels of libg2048.so on a batch of one board; this class only marshals the
-4x4 int64 `Matrix` to and from the device.  What differs from the reference, by design:
+by libg2048.so's g2048_one kernel (one launch + one stream synchronisation per method call, the
+Matrix travelling through a pinned zero-copy block); this class only marshals the 4x4 `Matrix`.  What differs from the reference, by design:
 the spawn RNG is the counter-based Philox stream of include/g2048.h keyed by `seed`
 (the reference draws from numpy's PCG64, which no reference test pins — SURVEY.md §8c).
 """
@@ -70,21 +70,23 @@ def _box(low, high, shape, dtype):
 
 
 class _Device:
-    """Per-process scratch for one-board launches (device buffers + the loaded library)."""
+    """Per-process state of the single-env path: the loaded library and ONE packed in/out block (G2048OneIO) in
+    pinned host memory that the kernel reads and writes in place (zero copy).  Every method of Game2048Env is one
+    g2048_one call = one kernel launch + one stream synchronisation; nothing else touches the device."""
     _inst = None
 
     def __init__(self):
         if not torch.cuda.is_available():
             raise _lib.G2048Error("Game2048Env needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.lib()
-        self.dev = torch.device("cuda", int(os.environ.get("G2048_DEVICE", torch.cuda.current_device())))
-        d = self.dev
-        self.values = torch.zeros(16, dtype=torch.int64, device=d)
-        self.obs = torch.zeros((16, 4, 4), dtype=torch.int64, device=d)
-        self.boards = torch.zeros(64, dtype=torch.uint8, device=d)          # 4 boards (one per direction)
-        self.u8 = torch.zeros(64, dtype=torch.uint8, device=d)              # small byte outputs
-        self.i32 = torch.zeros(8, dtype=torch.int32, device=d)
-        self.f32 = torch.zeros(1, dtype=torch.float32, device=d)
+        self.index = int(os.environ.get("G2048_DEVICE", torch.cuda.current_device()))
+        self.dev = torch.device("cuda", self.index)
+        self.buf = torch.zeros(C.sizeof(_lib.OneIO) + 64, dtype=torch.uint8).pin_memory()
+        base = (self.buf.data_ptr() + 63) // 64 * 64
+        self.io = _lib.OneIO.from_address(base)
+        self.ptr = C.c_void_p(base)
+        self.values = np.ctypeslib.as_array(self.io.values)                    # int64 [16]: the Matrix, in/out
+        self.obs = np.ctypeslib.as_array(self.io.obs).reshape(16, 4, 4)        # int64 [16,4,4]: stack(Matrix), out
 
     @classmethod
     def get(cls):
@@ -92,29 +94,33 @@ class _Device:
             cls._inst = cls()
         return cls._inst
 
-    def stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
-
-
-def _ptr(t, offset=0):
-    return C.c_void_p(t.data_ptr() + offset)
+    def call(self, op, matrix, action=0, trial=False, seed=0, index=0, illegal_move_reward=0.0, max_tile_exp=0,
+             need_valid=True):
+        """values <- matrix; run `op`; returns the io block (results valid until the next call)."""
+        if matrix is not None:
+            self.values[:] = np.asarray(matrix).reshape(16)
+        args = (self.ptr, op, int(action) & 3, 1 if trial else 0, seed, index, float(illegal_move_reward),
+                int(max_tile_exp))
+        if torch.cuda.current_device() == self.index:
+            rc = self.lib.g2048_one(*args, torch.cuda.current_stream(self.dev).cuda_stream, 1)
+        else:
+            with torch.cuda.device(self.index):
+                rc = self.lib.g2048_one(*args, torch.cuda.current_stream(self.dev).cuda_stream, 1)
+        check(rc)
+        if need_valid and self.io.bad_cells:
+            raise ValueError("board holds a cell that is not 0 or a power of two: %s" % (np.asarray(matrix),))
+        return self.io
 
 
 def stack(flat, layers=15):
     """[4,4] tile values -> [layers+1,4,4] one-hot (reference :17-32): channel 0 = empty,
-    channel k = (cell == 2**k).  Computed by g2048_encode_obs for the default 15 layers."""
+    channel k = (cell == 2**k); any other value lights no channel.  One g2048_one call."""
     flat = np.asarray(flat)
     if layers != 15 or flat.shape != (4, 4):
         raise ValueError("stack() supports the reference's 4x4 board with layers=15")
     d = _Device.get()
-    with torch.cuda.device(d.dev):
-        d.values.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.int64).reshape(16)))
-        # cells that are not 0 / a power of two light no channel in the reference either
-        check(d.lib.g2048_exp_from_values(_ptr(d.values), _ptr(d.boards), 16, None, d.stream()))
-        bad = (d.values != 0) & (d.boards[:16] == 0)
-        d.boards[:16].masked_fill_(bad, 63)
-        check(d.lib.g2048_encode_obs(_ptr(d.boards), _ptr(d.obs), _lib.OBS_I64, 1, d.stream()))
-        return d.obs.cpu().numpy().astype(int)
+    d.call(_lib.ONE_STATUS, flat, need_valid=False)
+    return d.obs.astype(int)
 
 
 class Game2048Env(_EnvBase):
@@ -166,49 +172,32 @@ class Game2048Env(_EnvBase):
     def close(self):
         pass
 
-    # -- device marshalling --------------------------------------------------------------
-    def _upload(self, d, copies=1):
-        v = torch.from_numpy(np.ascontiguousarray(self.Matrix, dtype=np.int64).reshape(16))
-        d.values.copy_(v)
-        bad = d.i32[7:8]
-        bad.zero_()
-        check(d.lib.g2048_exp_from_values(_ptr(d.values), _ptr(d.boards), 16, _ptr(bad), d.stream()))
-        if int(bad.item()):
-            raise ValueError("board holds a cell that is not 0 or a power of two: %s" % (self.Matrix,))
-        for k in range(1, copies):
-            d.boards[16 * k:16 * k + 16].copy_(d.boards[:16])
-
-    def _download(self, d, offset=0):
-        check(d.lib.g2048_values_from_exp(_ptr(d.boards, offset), _ptr(d.values), 16, d.stream()))
-        # write through the caller's array: set_board() aliases it (:286-288)
-        self.Matrix[...] = d.values.cpu().numpy().reshape(4, 4)
+    def _write_back(self, d):
+        # through the caller's array: set_board() aliases it (:286-288) and move() mutates it in place
+        self.Matrix[...] = d.values.reshape(4, 4)
 
     # -- gymnasium interface -------------------------------------------------------------
     def step(self, action):
-        """(:76-100) move, add a tile, detect the end.  An illegal move terminates (:91-95)."""
+        """(:76-100) move, add a tile, detect the end.  An illegal move terminates (:91-95).
+        One kernel launch: the Matrix goes in and the new Matrix, reward, flags, highest and the
+        observation come back in the same pinned block."""
         d = _Device.get()
         info = {'illegal_move': False}
-        with torch.cuda.device(d.dev):
-            self._upload(d)
-            d.u8[0] = int(action) & 3
-            a = _lib.StepArgs(_ptr(d.boards), _ptr(d.u8, 0), _ptr(d.f32), _ptr(d.u8, 16), _ptr(d.u8, 17),
-                              _ptr(d.u8, 18), None, None, None, None, None, None, None, None,
-                              1, 0, self._seed, self._step_index,
-                              float(self.illegal_move_reward), tile_to_exp(self.max_tile), 0)
-            check(d.lib.g2048_step(C.byref(a), d.stream()))
-            self._step_index += 1
-            self._download(d)
-            flags = d.u8[16:19].cpu().numpy()
-            reward = float(d.f32.item())
-        terminated = bool(flags[0])
-        if flags[1]:
+        io = d.call(_lib.ONE_STEP, self.Matrix, action=action, seed=self._seed, index=self._step_index,
+                    illegal_move_reward=self.illegal_move_reward, max_tile_exp=tile_to_exp(self.max_tile))
+        self._step_index += 1
+        terminated = bool(io.done)
+        if io.illegal:
             info['illegal_move'] = True
             reward = self.illegal_move_reward
         else:
+            reward = float(io.reward)
             assert reward <= 2**(self.w * self.h)                                          # :87
             self.score += reward
-        info['highest'] = self.highest()
-        return stack(self.Matrix), reward, terminated, False, info
+            self._write_back(d)
+        e = int(io.highest_exp)
+        info['highest'] = np.int64((1 << e) if e else 0)                                   # :97
+        return d.obs.astype(int), reward, terminated, False, info
 
     def reset(self, seed=None, options=None):
         """(:102-111) zero board, score 0, two tiles.  `seed` re-keys the draw stream."""
@@ -219,13 +208,12 @@ class Game2048Env(_EnvBase):
             self._step_index = 0
             self._reset_index = 0
         d = _Device.get()
-        with torch.cuda.device(d.dev):
-            check(d.lib.g2048_reset(_ptr(d.boards), None, 1, 0, self._seed, self._reset_index, d.stream()))
-            self._reset_index += 1
-            self.Matrix = np.zeros((self.h, self.w), int)
-            self._download(d)
+        d.call(_lib.ONE_RESET, None, seed=self._seed, index=self._reset_index)
+        self._reset_index += 1
+        self.Matrix = np.zeros((self.h, self.w), int)
+        self._write_back(d)
         self.score = 0
-        return stack(self.Matrix), {}
+        return d.obs.astype(int), {}
 
     def render(self, mode=None):
         if mode is None:
@@ -241,11 +229,9 @@ class Game2048Env(_EnvBase):
         """(:166-176) spawn a 2 (P=0.9) or 4 on a uniformly chosen empty cell."""
         assert (np.asarray(self.Matrix) == 0).any(), "No empty cell found"                 # :176
         d = _Device.get()
-        with torch.cuda.device(d.dev):
-            self._upload(d)
-            check(d.lib.g2048_add_tile(_ptr(d.boards), 1, 0, self._seed, self._step_index, d.stream()))
-            self._step_index += 1
-            self._download(d)
+        d.call(_lib.ONE_ADD_TILE, self.Matrix, seed=self._seed, index=self._step_index)
+        self._step_index += 1
+        self._write_back(d)
 
     def get(self, x, y):
         return self.Matrix[x, y]
@@ -257,64 +243,44 @@ class Game2048Env(_EnvBase):
         return np.argwhere(self.Matrix == 0)
 
     def _status(self):
-        d = _Device.get()
-        with torch.cuda.device(d.dev):
-            self._upload(d)
-            check(d.lib.g2048_status(_ptr(d.boards), _ptr(d.u8, 0), _ptr(d.u8, 1), _ptr(d.u8, 2), _ptr(d.u8, 3),
-                                     tile_to_exp(self.max_tile), 1, d.stream()))
-            return d.u8[:4].cpu().numpy()        # legal mask, highest exp, empties, isend
+        return _Device.get().call(_lib.ONE_STATUS, self.Matrix, max_tile_exp=tile_to_exp(self.max_tile))
 
     def highest(self):
         """(:190-192) the highest tile on the board (numpy int, like np.max)."""
-        e = int(self._status()[1])
+        e = int(self._status().highest_exp)
         return np.int64((1 << e) if e else 0)
 
     def legal_actions(self):
         """Bit mask of legal moves (bit d <=> move(d, trial=True) does not raise)."""
-        return int(self._status()[0])
+        return int(self._status().legal_mask)
 
     def move(self, direction, trial=False):
         """(:194-241) slide/merge toward 0=up 1=right 2=down 3=left; returns the score, raises
         IllegalMove when nothing moves.  trial=True leaves the board untouched."""
         d = _Device.get()
-        with torch.cuda.device(d.dev):
-            self._upload(d)
-            d.u8[0] = int(direction) & 3
-            check(d.lib.g2048_move(_ptr(d.boards), None if trial else _ptr(d.boards), _ptr(d.u8, 0),
-                                   _ptr(d.i32), _ptr(d.u8, 16), 1, d.stream()))
-            changed = bool(d.u8[16].item())
-            score = int(d.i32[0].item())
-            if changed and not trial:
-                self._download(d)
-        if not changed:
+        io = d.call(_lib.ONE_MOVE, self.Matrix, action=direction, trial=trial)
+        if not io.changed:
             raise IllegalMove
-        return score
+        if not trial:
+            self._write_back(d)
+        return int(io.score)
 
     def shift(self, row):
         """(:243-260) compact and combine one line toward index 0: ([4 values], score)."""
         row = [int(v) for v in row]
         assert len(row) == self.size
         d = _Device.get()
-        with torch.cuda.device(d.dev):
-            vals = torch.zeros(16, dtype=torch.int64)
-            vals[:4] = torch.tensor(row, dtype=torch.int64)          # the line as row 0, moved Left
-            d.values.copy_(vals)
-            bad = d.i32[7:8]
-            bad.zero_()
-            check(d.lib.g2048_exp_from_values(_ptr(d.values), _ptr(d.boards), 16, _ptr(bad), d.stream()))
-            if int(bad.item()):
-                raise ValueError("shift() needs tile values that are 0 or powers of two")
-            d.u8[0] = 3
-            check(d.lib.g2048_move(_ptr(d.boards), _ptr(d.boards), _ptr(d.u8, 0), _ptr(d.i32), None, 1,
-                                   d.stream()))
-            check(d.lib.g2048_values_from_exp(_ptr(d.boards), _ptr(d.values), 16, d.stream()))
-            out = d.values[:4].cpu().tolist()
-            score = int(d.i32[0].item())
-        return (out, score)
+        board = np.zeros(16, np.int64)
+        board[:4] = row                                              # the line as row 0, moved Left
+        try:
+            io = d.call(_lib.ONE_MOVE, board, action=3)
+        except ValueError:
+            raise ValueError("shift() needs tile values that are 0 or powers of two")
+        return ([int(v) for v in d.values[:4]], int(io.score))
 
     def isend(self):
         """(:262-280) max_tile reached, or no empty cell and no legal move."""
-        return bool(self._status()[3])
+        return bool(self._status().is_end)
 
     def get_board(self):
         return self.Matrix

@@ -4,8 +4,9 @@ Replaces `make_vec_env("2048-v0", n_envs)` at `/root/reference/ppo_train.py:123`
 DummyVecEnv + Monitor: a Python loop over env objects) with one kernel launch per step.
 Semantics kept from SB3: `step_wait()` -> (obs, rewards float32, dones bool, infos), same-step
 auto-reset with `infos[i]["terminal_observation"]`, `["TimeLimit.truncated"] = False`,
-`["episode"] = {"r", "l", "t"}` at episode end, plus the reference's `["highest"]` and
-`["illegal_move"]` (ppo_train.py:76-82 reads `infos[i]["highest"]` on done).  Info dicts are
+`["episode"] = {"r", "l", "t"}` at episode end (`r` = the sum of the episode's REWARDS, illegal-move penalty
+included, as Monitor computes it; the game score — merge scores only — is `["score"]`), plus the reference's
+`["highest"]` and `["illegal_move"]` (ppo_train.py:76-82 reads `infos[i]["highest"]` on done).  Info dicts are
 materialised only for envs that finished; all others share one read-only empty-ish dict, so
 the per-step Python cost does not grow with the batch.
 
@@ -79,7 +80,8 @@ class Game2048VecEnv(_VecEnvBase):
             idx_c = idx.cpu().numpy()
             term_obs = g.observe(self.obs_dtype, boards=r.terminal_boards[idx].contiguous())
             term_obs = term_obs if self.return_torch else term_obs.cpu().numpy()
-            fs = r.final_score[idx].cpu().numpy()
+            fr = r.final_return[idx].cpu().numpy()       # Monitor's 'r': the sum of the rewards the agent saw
+            fs = r.final_score[idx].cpu().numpy()        # the game score (merge scores only)
             fl = r.final_len[idx].cpu().numpy()
             hi = r.highest_exp[idx].cpu().numpy().astype(np.int64)
             il = r.illegal[idx].cpu().numpy()
@@ -88,7 +90,8 @@ class Game2048VecEnv(_VecEnvBase):
                 infos[i] = {
                     "TimeLimit.truncated": False,
                     "terminal_observation": term_obs[j],
-                    "episode": {"r": float(fs[j]), "l": int(fl[j]), "t": now},
+                    "episode": {"r": round(float(fr[j]), 6), "l": int(fl[j]), "t": now},
+                    "score": int(fs[j]),
                     "highest": int(1 << hi[j]) if hi[j] else 0,
                     "illegal_move": bool(il[j]),
                 }

@@ -52,9 +52,11 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 3 /* 2: G2048StepArgs.boards_out, data-side entry points */
+#define G2048_ABI_VERSION 4 /* 2: G2048StepArgs.boards_out, data-side entry points */
                             /* 3: draw stream version 2, g2048_philox2x32, g2048_draw_words, */
                             /*    g2048_step_many                                            */
+                            /* 4: G2048StepArgs.ep_return/final_return, g2048_step_n,        */
+                            /*    g2048_one (single-env packed call)                         */
 
 #define G2048_TAG_STEP   0u
 #define G2048_TAG_RESET  1u
@@ -119,12 +121,43 @@ typedef struct G2048StepArgs {
                                    /*        to the agent are written; NULL = in place.    */
                                    /*        Lets a rollout/trajectory buffer slice t+1 be */
                                    /*        produced from slice t with no copy.           */
+  float*          ep_return;       /* [n]    in/out, nullable: running sum of the REWARDS  */
+                                   /*        the step emitted (illegal_move_reward included */
+                                   /*        — what SB3's Monitor sums, ppo_train.py:123)   */
+  float*          final_return;    /* [n]    out, nullable: that sum, where done           */
 } G2048StepArgs;
 
 int g2048_abi_version(void);
 const char* g2048_last_error(void);
 
 int g2048_step(const G2048StepArgs* args, void* stream);
+
+/*
+ * n_steps consecutive steps of the same boards, ONE KERNEL LAUNCH PER STEP (each step reads
+ * and writes the boards in device memory, 38 algorithmic bytes per board like g2048_step),
+ * issued back to back from C as programmatic dependent launches.  Exactly what this loop does
+ * — which is the loop SB3's DummyVecEnv runs behind ppo_train.py:123, minus the interpreter
+ * between two steps:
+ *     for (k = 0; k < n_steps; ++k) { g2048_step(&a, stream); advance(a); }
+ * where advance() moves every PER-STEP array on by row_stride elements (actions, rewards,
+ * dones, illegal, highest_exp, legal_mask, final_score, final_len, final_return; boards for
+ * terminal_boards; 4 words for forced_draws) and step_index by 1; the per-env state (boards,
+ * ep_score, ep_len, ep_return) stays.  row_stride = 0 reuses the same rows every step;
+ * otherwise row_stride >= n.  boards_out and step_counter must be NULL.
+ * Use: open-loop action sequences stepped at the launch rate of C instead of the caller's
+ * language (a 131,072-board shard is stepped in ~3 us; a Python loop issues a launch every
+ * ~6 us).  g2048_step_many is the variant that also keeps the boards in registers.
+ */
+int g2048_step_n(const G2048StepArgs* args, uint32_t n_steps, uint64_t row_stride, void* stream);
+
+/*
+ * A caller-built list of `count` complete g2048_step calls (each element with its own
+ * boards, per-step rows, env_id_base, step_index ...), launched in order on `stream` by ONE
+ * call — the general form of g2048_step_n: the elements may step different env sets (several
+ * vectorised envs stepped round-robin) or the same one (then element j+1 must carry
+ * step_index + 1).  Fails on the first invalid element; earlier elements stay launched.
+ */
+int g2048_step_list(const G2048StepArgs* list, uint64_t count, void* stream);
 
 /*
  * n_steps steps in one launch, for open-loop action sequences (pre-generated random
@@ -214,6 +247,47 @@ int g2048_values_from_exp(const uint8_t* boards, int64_t* values, uint64_t n_cel
                           void* stream);
 int g2048_exp_from_values(const int64_t* values, uint8_t* boards, uint64_t n_cells,
                           uint32_t* bad_count, void* stream);
+
+/*
+ * ONE env per call: the reference's single-env class (game2048_env.py:34-288) on a packed
+ * in/out block that may live in pinned HOST memory (cudaHostAlloc: the device reads and
+ * writes it in place, zero copy), so a call costs one launch and — with synchronize != 0 —
+ * one stream synchronisation.  `values` is the reference's Matrix (tile VALUES, row-major).
+ *   G2048_ONE_STEP      step(action) (:76-100) without auto-reset: move, spawn with the step-tag
+ *                       draw word of (seed, env 0, index), isend; an illegal move leaves values
+ *                       untouched, sets illegal/done and reward = illegal_move_reward
+ *   G2048_ONE_RESET     reset() (:102-111): values = fresh board from the reset-tag words at `index`
+ *   G2048_ONE_MOVE      move(action, trial) (:194-241): no spawn; changed == 0 is IllegalMove;
+ *                       values are written only when changed and trial == 0; reward = score
+ *   G2048_ONE_ADD_TILE  add_tile() (:166-176) with the step-tag word at `index`
+ *   G2048_ONE_STATUS    nothing moves: only the queries below
+ * Every op also fills highest_exp (:190-192), n_empty (:186-188), is_end (:262-280),
+ * legal_mask and obs = stack(values) (:17-32, int64 [16][4][4]) of the values as they are
+ * after the op.  Cells that are not 0 or a power of two 2..2^31 are counted in bad_cells; a
+ * board with such cells is not stepped/moved (obs still follows the reference: they light no
+ * channel).
+ */
+#define G2048_ONE_STEP     0
+#define G2048_ONE_RESET    1
+#define G2048_ONE_MOVE     2
+#define G2048_ONE_ADD_TILE 3
+#define G2048_ONE_STATUS   4
+typedef struct G2048OneIO {
+  int64_t  values[16];   /* in/out */
+  int64_t  obs[256];     /* out    */
+  float    reward;       /* out: STEP merge score or illegal_move_reward; MOVE score */
+  uint32_t score;        /* out: merge score of the move                             */
+  uint8_t  done;         /* out: STEP terminated                                     */
+  uint8_t  illegal;      /* out: STEP info['illegal_move']                           */
+  uint8_t  changed;      /* out: the op changed the board                            */
+  uint8_t  highest_exp;  /* out */
+  uint8_t  legal_mask;   /* out */
+  uint8_t  n_empty;      /* out */
+  uint8_t  is_end;       /* out */
+  uint8_t  bad_cells;    /* out */
+} G2048OneIO;
+int g2048_one(G2048OneIO* io, int op, int action, int trial, uint64_t seed, uint64_t index,
+              float illegal_move_reward, uint32_t max_tile_exp, void* stream, int synchronize);
 
 /* Debug: out[4*i..4*i+3] = philox4x32_10(ctr[4*i..], key) — known-answer tests. */
 int g2048_philox(const uint32_t* ctr, uint32_t key0, uint32_t key1, uint32_t* out,

@@ -197,8 +197,10 @@ static void step_one(const G2048StepArgs* a, uint64_t i) {
     score = 0;
   }
   uint32_t es = 0, el = 0;
+  float er = 0.f;
   if (a->ep_score) es = a->ep_score[i] + score;                   /* :86 */
   if (a->ep_len) el = a->ep_len[i] + 1;
+  if (a->ep_return) er = a->ep_return[i] + reward;                /* SB3 Monitor.step: rewards.append(reward); sum at done (ppo_train.py:123) */
   a->rewards[i] = reward;
   a->dones[i] = (uint8_t)terminated;
   if (a->illegal) a->illegal[i] = (uint8_t)illegal;
@@ -207,13 +209,15 @@ static void step_one(const G2048StepArgs* a, uint64_t i) {
     if (a->terminal_boards) memcpy(a->terminal_boards + 16 * i, b, 16);
     if (a->final_score) a->final_score[i] = es;
     if (a->final_len) a->final_len[i] = el;
+    if (a->final_return) a->final_return[i] = er;
     if (a->flags & G2048_FLAG_AUTO_RESET) {
       reset_board(b, w);
-      es = 0; el = 0;
+      es = 0; el = 0; er = 0.f;
     }
   }
   if (a->ep_score) a->ep_score[i] = es;
   if (a->ep_len) a->ep_len[i] = el;
+  if (a->ep_return) a->ep_return[i] = er;
   if (a->legal_mask) a->legal_mask[i] = legal_mask_of(b);
 }
 

@@ -23,6 +23,7 @@ class StepArgs(C.Structure):
         ("step_index", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
+        ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
     ]
 
 
@@ -75,6 +76,7 @@ class OracleBatch:
         self.boards = np.zeros((self.n, 16), np.uint8)
         self.ep_score = np.zeros(self.n, np.uint32)
         self.ep_len = np.zeros(self.n, np.uint32)
+        self.ep_return = np.zeros(self.n, np.float32)
         self.step_index = 0
         self.reset_index = 0
 
@@ -88,9 +90,11 @@ class OracleBatch:
         if mask is None:
             self.ep_score[:] = 0
             self.ep_len[:] = 0
+            self.ep_return[:] = 0
         else:
             self.ep_score[m != 0] = 0
             self.ep_len[m != 0] = 0
+            self.ep_return[m != 0] = 0
         return self.boards
 
     def step(self, actions, forced_draws=None):
@@ -101,6 +105,7 @@ class OracleBatch:
             illegal=np.zeros(n, np.uint8), highest_exp=np.zeros(n, np.uint8),
             legal_mask=np.zeros(n, np.uint8), terminal_boards=np.zeros((n, 16), np.uint8),
             final_score=np.zeros(n, np.uint32), final_len=np.zeros(n, np.uint32),
+            final_return=np.zeros(n, np.float32),
         )
         fd = None if forced_draws is None else np.ascontiguousarray(forced_draws, dtype=np.uint32)
         a = StepArgs(_p(self.boards), _p(actions), _p(out["rewards"]), _p(out["dones"]),
@@ -108,7 +113,8 @@ class OracleBatch:
                      _p(out["terminal_boards"]), _p(self.ep_score), _p(self.ep_len),
                      _p(out["final_score"]), _p(out["final_len"]), _p(fd), None,
                      n, self.env_id_base, self.seed, self.step_index,
-                     self.illegal_move_reward, self.max_tile_exp, self.flags)
+                     self.illegal_move_reward, self.max_tile_exp, self.flags, None,
+                     _p(self.ep_return), _p(out["final_return"]))
         if self.threads > 1:
             rc = lib().g2048_oracle_step_mt(C.byref(a), C.c_int(self.threads))
         else:

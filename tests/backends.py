@@ -43,6 +43,7 @@ class SimBatch(oracle.OracleBatch):
         sel = slice(None) if mask is None else (m != 0)
         self.ep_score[sel] = 0
         self.ep_len[sel] = 0
+        self.ep_return[sel] = 0
         return self.boards
 
     def step(self, actions, forced_draws=None):
@@ -53,6 +54,7 @@ class SimBatch(oracle.OracleBatch):
             illegal=np.zeros(n, np.uint8), highest_exp=np.zeros(n, np.uint8),
             legal_mask=np.zeros(n, np.uint8), terminal_boards=np.zeros((n, 16), np.uint8),
             final_score=np.zeros(n, np.uint32), final_len=np.zeros(n, np.uint32),
+            final_return=np.zeros(n, np.float32),
         )
         fd = None if forced_draws is None else np.ascontiguousarray(forced_draws, dtype=np.uint32)
         a = oracle.StepArgs(_p(self.boards), _p(actions), _p(out["rewards"]), _p(out["dones"]),
@@ -60,7 +62,8 @@ class SimBatch(oracle.OracleBatch):
                             _p(out["terminal_boards"]), _p(self.ep_score), _p(self.ep_len),
                             _p(out["final_score"]), _p(out["final_len"]), _p(fd), None,
                             n, self.env_id_base, self.seed, self.step_index,
-                            self.illegal_move_reward, self.max_tile_exp, self.flags)
+                            self.illegal_move_reward, self.max_tile_exp, self.flags, None,
+                            _p(self.ep_return), _p(out["final_return"]))
         assert sim_lib().sim_step(C.byref(a)) == 0
         self.step_index += 1
         out["boards"] = self.boards
@@ -154,6 +157,10 @@ class GpuBatch:
     def ep_len(self):
         return self.g.ep_len.cpu().numpy().astype(np.uint32)
 
+    @property
+    def ep_return(self):
+        return self.g.ep_return.cpu().numpy()
+
     def reset(self, mask=None):
         import torch
         m = None if mask is None else torch.as_tensor(np.ascontiguousarray(mask, dtype=np.uint8))
@@ -167,7 +174,8 @@ class GpuBatch:
         return dict(boards=c(r.boards, np.uint8), rewards=c(r.rewards, np.float32), dones=c(r.dones, np.uint8),
                     illegal=c(r.illegal, np.uint8), highest_exp=c(r.highest_exp, np.uint8),
                     legal_mask=c(r.legal_mask, np.uint8), terminal_boards=c(r.terminal_boards, np.uint8),
-                    final_score=c(r.final_score, np.uint32), final_len=c(r.final_len, np.uint32))
+                    final_score=c(r.final_score, np.uint32), final_len=c(r.final_len, np.uint32),
+                    final_return=c(r.final_return, np.float32))
 
 
 class _BoardsView:

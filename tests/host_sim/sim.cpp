@@ -44,15 +44,18 @@ extern "C" int sim_step(const G2048StepArgs* p) {
     if (p->illegal) p->illegal[i] = !o.legal;
     if (p->highest_exp) p->highest_exp[i] = (uint8_t)o.highest;
     uint32_t es = p->ep_score ? p->ep_score[i] + (uint32_t)o.score : 0, el = p->ep_len ? p->ep_len[i] + 1 : 0;
+    float er = p->ep_return ? p->ep_return[i] + p->rewards[i] : 0.f;
     if (o.done) {
       const uint32_t t[4] = {o.t0, o.t1, o.t2, o.t3};
       if (p->terminal_boards) store(p->terminal_boards + 16 * i, t);
       if (p->final_score) p->final_score[i] = es;
       if (p->final_len) p->final_len[i] = el;
-      if (auto_reset) es = el = 0;
+      if (p->final_return) p->final_return[i] = er;
+      if (auto_reset) { es = el = 0; er = 0.f; }
     }
     if (p->ep_score) p->ep_score[i] = es;
     if (p->ep_len) p->ep_len[i] = el;
+    if (p->ep_return) p->ep_return[i] = er;
     if (p->legal_mask) p->legal_mask[i] = (uint8_t)legal_mask(r[0], r[1], r[2], r[3]);
   }
   if (p->step_counter) *p->step_counter += 1;

@@ -79,6 +79,7 @@ def check_rollouts(ops, rollouts, max_steps=None):
             T = min(T, max_steps)
         b = ops.Batch(**cfg)
         assert np.array_equal(b.reset(), rec["init_boards"]), name
+        ep_ret = np.zeros(cfg["n"], np.float32)        # SB3 Monitor's running sum, from the REFERENCE's own rewards
         for t in range(T):
             out = b.step(rec["actions"][t])
             out["ep_score"], out["ep_len"] = b.ep_score, b.ep_len
@@ -87,6 +88,11 @@ def check_rollouts(ops, rollouts, max_steps=None):
             d = rec["dones"][t] != 0
             for k in DONE_KEYS:
                 assert np.array_equal(out[k][d], rec[k][t][d]), (name, t, k)
+            ep_ret += rec["rewards"][t]
+            assert np.array_equal(out["final_return"][d], ep_ret[d]), (name, t, "final_return")
+            if cfg["auto_reset"]:
+                ep_ret[d] = 0
+            assert np.array_equal(b.ep_return, ep_ret), (name, t, "ep_return")
 
 
 def check_against_oracle(ops, n=4096, steps=64, seed=7, policy="random", env_id_base=0, max_tile_exp=0,
@@ -109,10 +115,11 @@ def check_against_oracle(ops, n=4096, steps=64, seed=7, policy="random", env_id_
             act = rng.integers(0, 4, n).astype(np.uint8)
         oa, ob = a.step(act), b.step(act)
         oa["ep_score"], oa["ep_len"], ob["ep_score"], ob["ep_len"] = a.ep_score, a.ep_len, b.ep_score, b.ep_len
-        for k in STEP_KEYS:
+        oa["ep_return"], ob["ep_return"] = a.ep_return, b.ep_return
+        for k in STEP_KEYS + ("ep_return",):
             assert np.array_equal(oa[k], ob[k]), (t, k)
         d = oa["dones"] != 0
-        for k in DONE_KEYS:
+        for k in DONE_KEYS + ("final_return",):
             assert np.array_equal(oa[k][d], ob[k][d]), (t, k)
         mask = oa["legal_mask"]
     return a

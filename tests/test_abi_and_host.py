@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), name
     assert sorted(g._lib.EXPORTS) == names
-    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 3
+    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
@@ -42,6 +42,9 @@ def test_struct_layouts_match_header():
              sizeof(G2048EnvConfig), sizeof(G2048HostStepOut));
       printf("%zu %zu %zu %zu\n", sizeof(G2048StepManyArgs), offsetof(G2048StepManyArgs, n),
              offsetof(G2048StepManyArgs, n_steps), offsetof(G2048StepManyArgs, flags));
+      printf("%zu %zu %zu %zu %zu\n", offsetof(G2048StepArgs, boards_out), offsetof(G2048StepArgs, ep_return),
+             offsetof(G2048StepArgs, final_return), sizeof(G2048OneIO), offsetof(G2048OneIO, reward));
+      printf("%zu %zu\n", offsetof(G2048OneIO, done), offsetof(G2048OneIO, bad_cells));
       return 0;
     }'''
     d = os.path.join(ROOT, "tests", "host_sim")
@@ -55,6 +58,10 @@ def test_struct_layouts_match_header():
     assert C.sizeof(g._lib.EnvConfig) == out[4] and C.sizeof(g._lib.HostStepOut) == out[5]
     M = g._lib.StepManyArgs
     assert [C.sizeof(M), M.n.offset, M.n_steps.offset, M.flags.offset] == out[6:10]
+    O = g._lib.OneIO
+    for S in (g._lib.StepArgs, oracle.StepArgs):
+        assert [S.boards_out.offset, S.ep_return.offset, S.final_return.offset] == out[10:13]
+    assert [C.sizeof(O), O.reward.offset, O.done.offset, O.bad_cells.offset] == [out[13], out[14], out[15], out[16]]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

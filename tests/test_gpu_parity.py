@@ -301,3 +301,177 @@ def test_step_many_device_policy_is_sample_actions_plus_step(policy, n, K, base,
         r = loop.step(a)
         assert torch.equal(r.boards, traj[k]) and torch.equal(r.rewards, rewards[k])
     assert torch.equal(fused.boards, loop.boards) and torch.equal(fused.legal_mask, loop.legal_mask)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: specialised output sets, g2048_step_n, graph capture, real multi-GPU sharding
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("outputs", [
+    (),                                                   # lean kernel
+    ("legal_mask",),                                      # O_MASK kernel (BASELINE config 4)
+    ("illegal", "highest", "legal_mask"),                 # the evaluator's kernel
+    ("illegal", "highest", "legal_mask", "episode", "terminal"),   # Game2048VecEnv's kernel
+    ("illegal",), ("episode",), ("highest", "terminal"),  # odd combinations: the generic (nullable-pointer) kernel
+])
+def test_every_output_set_matches_the_oracle(outputs):
+    """Each compile-time output set the library instantiates (and the generic kernel behind any other
+    combination) against the oracle: boards, rewards, dones always; the optional outputs that were asked for."""
+    import torch
+    import gym_2048_b200 as g
+    n, T = 70001, 80                                       # ragged: partial last warp, several boards per thread at 1024x148? no: small shape
+    gm = g.BatchedGame2048(n, seed=21, env_id_base=5, outputs=outputs, illegal_move_reward=-1.0, max_tile=64)
+    ref = oracle.OracleBatch(n, seed=21, env_id_base=5, illegal_move_reward=-1.0, max_tile_exp=6, threads=4)
+    assert np.array_equal(gm.reset().cpu().numpy(), ref.reset())
+    rng = np.random.default_rng(2)
+    for t in range(T):
+        act = rng.integers(0, 4, n).astype(np.uint8)
+        r = gm.step(torch.from_numpy(act).cuda())
+        o = ref.step(act)
+        d = o["dones"] != 0
+        assert np.array_equal(r.boards.cpu().numpy(), ref.boards), t
+        assert np.array_equal(r.rewards.cpu().numpy(), o["rewards"]) and np.array_equal(r.dones.cpu().numpy(), d)
+        if "illegal" in outputs:
+            assert np.array_equal(r.illegal.cpu().numpy(), o["illegal"] != 0)
+        if "highest" in outputs:
+            assert np.array_equal(r.highest_exp.cpu().numpy(), o["highest_exp"])
+        if "legal_mask" in outputs:
+            assert np.array_equal(r.legal_mask.cpu().numpy(), o["legal_mask"])
+        if "terminal" in outputs:
+            assert np.array_equal(r.terminal_boards.cpu().numpy()[d], o["terminal_boards"][d])
+        if "episode" in outputs:
+            assert np.array_equal(gm.ep_score.cpu().numpy().astype(np.uint32), ref.ep_score)
+            assert np.array_equal(gm.ep_len.cpu().numpy().astype(np.uint32), ref.ep_len)
+            assert np.array_equal(gm.ep_return.cpu().numpy(), ref.ep_return)
+            assert np.array_equal(r.final_score.cpu().numpy().astype(np.uint32)[d], o["final_score"][d])
+            assert np.array_equal(r.final_len.cpu().numpy().astype(np.uint32)[d], o["final_len"][d])
+            assert np.array_equal(r.final_return.cpu().numpy()[d], o["final_return"][d])
+
+
+@pytest.mark.parametrize("n,K,outputs", [
+    (1, 3, ()), (1000, 17, ("legal_mask",)), (131072, 24, ()), (70001, 9, ("illegal", "highest", "legal_mask", "episode")),
+])
+def test_step_n_is_k_calls_of_step(n, K, outputs):
+    """g2048_step_n (K launches issued from C) == K calls of step(): per-step rewards/dones/optional rows, final
+    boards, running episode statistics — against the product's own step() and, through it, the oracle."""
+    import torch
+    import gym_2048_b200 as g
+    mk = lambda: g.BatchedGame2048(n, seed=4, env_id_base=2**32 - 500, outputs=outputs, illegal_move_reward=-1.0)   # noqa: E731
+    a, b = mk(), mk()
+    a.reset(), b.reset()
+    acts = torch.randint(0, 4, (K, n), device="cuda", dtype=torch.uint8, generator=torch.Generator(device="cuda").manual_seed(1))
+    ill = torch.zeros((K, n), dtype=torch.uint8, device="cuda") if "illegal" in outputs else None
+    hi = torch.zeros((K, n), dtype=torch.uint8, device="cuda") if "highest" in outputs else None
+    lm = torch.zeros((K, n), dtype=torch.uint8, device="cuda") if "legal_mask" in outputs else None
+    rew, done = a.step_n(acts, illegal=ill, highest_exp=hi, legal_mask_out=lm)
+    for k in range(K):
+        r = b.step(acts[k])
+        assert torch.equal(rew[k], r.rewards) and torch.equal(done[k], r.dones), k
+        if ill is not None:
+            assert torch.equal(ill[k].bool(), r.illegal)
+        if hi is not None:
+            assert torch.equal(hi[k], r.highest_exp)
+        if lm is not None:
+            assert torch.equal(lm[k], r.legal_mask)
+    assert torch.equal(a.boards, b.boards) and a.step_index == b.step_index == K
+    if "legal_mask" in outputs:
+        assert torch.equal(a.legal_mask, b.legal_mask)
+    if "episode" in outputs:
+        assert torch.equal(a.ep_score, b.ep_score) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_return, b.ep_return)
+    ref = oracle.OracleBatch(n, seed=4, env_id_base=2**32 - 500, illegal_move_reward=-1.0, threads=4)
+    ref.reset()
+    for k in range(K):
+        ref.step(acts[k].cpu().numpy())
+    assert np.array_equal(a.boards.cpu().numpy(), ref.boards)
+
+
+def test_capture_replays_a_closed_loop_of_policy_and_step():
+    """BatchedGame2048.capture(): T x (device policy -> step) captured once, replayed R times == the same loop run
+    eagerly on a twin env (and the oracle): the device-side step index makes every replay draw fresh tiles."""
+    import torch
+    import gym_2048_b200 as g
+    n, T, R = 20000, 6, 5
+    mk = lambda: g.BatchedGame2048(n, seed=77, outputs=("legal_mask",))     # noqa: E731
+    a, b = mk(), mk()
+    a.reset(), b.reset()
+    acts = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    shift = torch.zeros(1, dtype=torch.uint8, device="cuda")
+
+    def policy(game, out):
+        # a deterministic closed-loop policy on the device: lowest legal move, rotated by a replay counter
+        m = game.legal_mask
+        first = torch.where(m & 1 != 0, 0, torch.where(m & 2 != 0, 1, torch.where(m & 4 != 0, 2, 3)))
+        out.copy_(((first + shift) & 3).to(torch.uint8))
+
+    def body():
+        for _ in range(T):
+            policy(a, acts)
+            a.step(acts)
+    replay = a.capture(body, warmup=1)
+    assert replay.steps == T
+    for r in range(R):
+        shift.fill_(r & 3)
+        replay()
+    torch.cuda.synchronize()
+    a.use_device_step_counter(False)
+    assert a.step_index == T * (R + 1)
+    ref = oracle.OracleBatch(n, seed=77)
+    ref.reset()
+    acts_b = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for r in range(-1, R):
+        shift.fill_(max(r, 0) & 3 if r >= 0 else 0)
+        for _ in range(T):
+            policy(b, acts_b)
+            b.step(acts_b)
+            ref.step(acts_b.cpu().numpy())
+    assert torch.equal(a.boards, b.boards)
+    assert np.array_equal(a.boards.cpu().numpy(), ref.boards)
+
+
+def test_sharding_invariance_on_two_real_gpus():
+    """SURVEY §8e on hardware: the same 1 Mi-id batch stepped as one batch on cuda:0 and as two halves on cuda:0 /
+    cuda:1 (env_id_base = rank * n/2) gives bit-identical boards, rewards and dones."""
+    import torch
+    import gym_2048_b200 as g
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, T = 1 << 18, 40
+    full = g.BatchedGame2048(n, seed=13, device="cuda:0", env_id_base=1000, outputs=("legal_mask",))
+    halves = [g.BatchedGame2048(n // 2, seed=13, device="cuda:%d" % r, env_id_base=1000 + r * (n // 2), outputs=("legal_mask",))
+              for r in range(2)]
+    full.reset()
+    for h in halves:
+        h.reset()
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    for t in range(T):
+        act = torch.randint(0, 4, (n,), device="cuda:0", dtype=torch.uint8, generator=gen)
+        rf = full.step(act)
+        rs = [h.step(act[r * (n // 2):(r + 1) * (n // 2)].to(h.device)) for r, h in enumerate(halves)]
+        for key in ("boards", "rewards", "dones", "legal_mask"):
+            got = torch.cat([getattr(x, key).to("cuda:0") for x in rs])
+            assert torch.equal(getattr(rf, key), got), (t, key)
+
+
+def test_step_schedule_equals_eager_round_robin():
+    """StepSchedule / g2048_step_list: K pre-built step calls over three env sets, issued by one C call in two
+    slices, == the same calls made one by one from Python."""
+    import torch
+    import gym_2048_b200 as g
+    n, K = 33000, 30
+    mk = lambda s: g.BatchedGame2048(n, seed=3, env_id_base=s * n, outputs=("legal_mask",) if s == 1 else ())   # noqa: E731
+    A, B = [mk(s) for s in range(3)], [mk(s) for s in range(3)]
+    for x in A + B:
+        x.reset()
+    acts = torch.randint(0, 4, (K, n), device="cuda", dtype=torch.uint8, generator=torch.Generator(device="cuda").manual_seed(2))
+    sched = g.StepSchedule()
+    for j in range(K):
+        sched.add(A[j % 3], acts[j])
+    assert len(sched) == K and A[0].step_index == K // 3
+    sched.run(0, 11)
+    sched.run()
+    with pytest.raises(g.G2048Error):
+        sched.run(0, 5)
+    for j in range(K):
+        B[j % 3].step(acts[j])
+    for a, b in zip(A, B):
+        assert torch.equal(a.boards, b.boards) and torch.equal(a.rewards, b.rewards) and torch.equal(a._dones, b._dones)
+    assert torch.equal(A[1].legal_mask, B[1].legal_mask)
