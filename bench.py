@@ -470,6 +470,43 @@ def run_ours(args):
     del games, pool
     torch.cuda.empty_cache()
 
+    # ---- BASELINE config 4 (N = 1 only): 262,144 envs returning the legal-action mask, auto-reset, actions uniform
+    #      among the legal moves — mid-game boards.  One launch per step: the step kernel draws the action from the
+    #      mask the previous step wrote, plays it and writes the new mask (step(policy="legal")).
+    config4 = None
+    if world == 1 and not args.no_config4:
+        n4, S4 = 262144, 16
+        g4 = [g.BatchedGame2048(n4, seed=42, device=dev, env_id_base=s * n4, outputs=("legal_mask",)) for s in range(S4)]
+        for gm in g4:
+            gm.reset()
+            gm.step_many(policy="legal", n_steps=200)               # play into the mid-game (mean ~5 empty cells)
+        acts4 = [torch.empty(n4, dtype=torch.uint8, device=dev) for _ in range(S4)]
+        K4, R4, spin4 = 50, 25, 4096
+        sched = g.StepSchedule()
+        for j in range(spin4 + R4 * K4):
+            sched.add(g4[j % S4], acts4[j % S4], policy="legal")
+        sched.build()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(R4 + 1)]
+        torch.cuda.synchronize()
+        sched.run(0, spin4)
+        ev[0].record()
+        for r in range(R4):
+            sched.run(spin4 + r * K4, spin4 + (r + 1) * K4)
+            ev[r + 1].record()
+        torch.cuda.synchronize()
+        m4 = statistics.median(ev[r].elapsed_time(ev[r + 1]) for r in range(R4)) / K4          # ms per step
+        empties = float((g4[0].boards == 0).sum(dim=1).float().mean())
+        bytes4 = 40                                   # board in 16 + mask in 1 + board out 16 + mask out 1 + action 1 + reward 4 + done 1
+        peak4 = hbm_peak()[0]
+        config4 = {"workload": "BASELINE config 4: %d envs, legal-action mask + auto-reset, actions uniform among the "
+                               "legal moves (drawn in the step kernel), %d env sets round-robin" % (n4, S4),
+                   "value": n4 / (m4 * 1e-3), "unit": UNIT, "us_per_step": m4 * 1e3, "launches_per_step": 1,
+                   "kernel": "g2048_step_kernel<O_MASK, false, POLICY_LEGAL>", "algorithmic_bytes_per_step": bytes4,
+                   "roofline_frac": bytes4 * n4 / (m4 * 1e-3) / 1e9 / peak4, "mean_empty_cells": empties,
+                   "issue": "g2048_step_list via StepSchedule", "steps": K4, "repeats": R4}
+        del g4, acts4, sched
+        torch.cuda.empty_cache()
+
     # ---- e2e: host buffers through the C-ABI handle, copies inside the timed region ----------
     Ke = max(3, min(K * R, args.e2e_steps))
     henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, n_chunks=args.e2e_chunks)
@@ -485,6 +522,22 @@ def run_ours(args):
     chk = float(henv.buffers.rewards.sum())        # the result is read on the host
     e2e_value = total_envs * Ke / e2e_s
     e2e_launches = henv.n_chunks_effective * Ke
+    henv.close()
+    # the same call with the compact host format (boards 4 bits per cell: 13 instead of 21 bytes per board come back)
+    henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, n_chunks=args.e2e_chunks, board_format="nibble")
+    henv.reset()
+    for i in range(5):
+        henv.step_pinned(host_pool[i % 8])
+    barrier()
+    t0 = time.perf_counter()
+    overflow = 0
+    for i in range(Ke):
+        overflow += henv.step_pinned(host_pool[i % 8]).nibble_overflow.value
+    e2c_s = max_over_ranks(time.perf_counter() - t0)
+    chk_c = float(henv.buffers.rewards.sum())
+    e2e_compact = {"value": total_envs * Ke / e2c_s, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 13,
+                   "steps": Ke, "ms_per_step": 1e3 * e2c_s / Ke, "boards_not_fitting": overflow, "checksum": chk_c,
+                   "api": "g2048_env_step_host, G2048_BOARDS_NIBBLE (boards 4 bits per cell, pinned host buffers)"}
     henv.close()
 
     if rank != 0:
@@ -513,8 +566,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,
                 "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "chunks": args.e2e_chunks,
                 "api": "g2048_env_step_host (pinned host buffers)", "checksum": chk},
+        "e2e_compact": e2e_compact,
         "weak": weak,
         "fused": fused,
+        "config4": config4,
         "gpu_launches": K * R, "e2e_gpu_launches": e2e_launches,
         "clocks": clocks,
         "gpu": torch.cuda.get_device_name(local),
@@ -563,6 +618,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=3)
     ap.add_argument("--ref-steps-per-proc", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 extra block (N = 1)")
     args = ap.parse_args()
     guard_stdout()
     if args.impl == "reference":

@@ -26,7 +26,7 @@ EXPORTS = [
     "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_n", "g2048_step_list", "g2048_one", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
-    "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_step_index",
+    "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_get_boards_host", "g2048_env_step_index",
     "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return", "g2048_gae",
     "g2048_csv_export", "g2048_csv_rows", "g2048_csv_import",
 ]
@@ -50,6 +50,7 @@ class StepArgs(C.Structure):
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
         ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
+        ("boards_nibble", C.c_void_p), ("nibble_overflow", C.c_void_p),
     ]
 
 
@@ -82,7 +83,7 @@ class EnvConfig(C.Structure):
         ("device", C.c_int32), ("flags", C.c_uint32), ("n", C.c_uint64),
         ("env_id_base", C.c_uint64), ("seed", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
-        ("n_chunks", C.c_uint32), ("reserved", C.c_uint32),
+        ("n_chunks", C.c_uint32), ("board_format", C.c_uint32),
     ]
 
 
@@ -91,7 +92,11 @@ class HostStepOut(C.Structure):
     _fields_ = [
         ("boards", C.c_void_p), ("rewards", C.c_void_p), ("dones", C.c_void_p),
         ("illegal", C.c_void_p), ("highest_exp", C.c_void_p), ("legal_mask", C.c_void_p),
+        ("nibble_overflow", C.c_void_p),
     ]
+
+
+BOARDS_BYTES, BOARDS_NIBBLE = 0, 1
 
 
 def _stale():
@@ -176,6 +181,7 @@ def lib():
     L.g2048_env_step_host.argtypes = [vp, vp, C.POINTER(HostStepOut)]
     L.g2048_env_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.g2048_env_set_boards_host.argtypes = [vp, vp]
+    L.g2048_env_get_boards_host.argtypes = [vp, vp]
     L.g2048_env_step_index.argtypes = [vp]
     L.g2048_sample_actions.argtypes = [vp, vp, u64, u64, u64, u64, vp]
     L.g2048_symmetry.argtypes = [vp, vp, vp, vp, vp, vp, u64, C.c_int, C.c_int, vp]

@@ -57,6 +57,7 @@ class StepResult:
     final_score: Optional[torch.Tensor] = None  # int32 [n] episode score, valid where dones
     final_len: Optional[torch.Tensor] = None    # int32 [n] episode length, valid where dones
     final_return: Optional[torch.Tensor] = None  # float32 [n] sum of the episode's rewards (SB3 Monitor 'r'), where dones
+    actions: Optional[torch.Tensor] = None      # uint8 [n] the actions played (step(policy=...): drawn by the kernel)
 
 
 class BatchedGame2048:
@@ -104,6 +105,7 @@ class BatchedGame2048:
         self.ep_return = torch.zeros(n, dtype=torch.float32, device=dev) if ep else None
         self.final_return = torch.zeros(n, dtype=torch.float32, device=dev) if ep else None
         self._step_counter = None      # device uint64 step index (use_device_step_counter)
+        self._actions_out = None       # where step(policy=...) writes the actions it drew
         self._args = None              # cached G2048StepArgs, rebuilt when a knob changes
 
     # -- knobs (reference :61-73) ------------------------------------------------------
@@ -200,8 +202,13 @@ class BatchedGame2048:
             raise ValueError("%s must be a contiguous uint8 [%d,16] tensor on %s" % (what, self.num_envs, self.device))
         return t
 
-    def step(self, actions, forced_draws=None, boards_out=None, terminal_out=None):
+    def step(self, actions=None, forced_draws=None, boards_out=None, terminal_out=None, policy=None):
         """One env step for every board.  `actions`: uint8/int tensor [n] on any device.
+
+        policy = "uniform" / "legal": the kernel draws the actions itself — exactly the actions sample_actions(legal=...)
+        would return for this step — and steps with them in the SAME launch (BASELINE config 4: sample a legal action,
+        step, hand back the new legal mask, one kernel per step); they are written to `actions` when given (a
+        contiguous uint8 [n] tensor on the device) or to an internal buffer, and come back as StepResult.actions.
 
         boards_out: step OUT OF PLACE — the boards handed back to the agent are written there
         and become the env's live state (`self.boards`), the previous buffer keeps the pre-step
@@ -211,10 +218,30 @@ class BatchedGame2048:
         The returned StepResult holds the env's own output tensors (overwritten by the next
         step); clone what must outlive it."""
         n = self.num_envs
-        if isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device \
+        pol = 0
+        if policy is not None:
+            if policy not in ("uniform", "legal"):
+                raise ValueError("policy must be None, 'uniform' or 'legal'")
+            if policy == "legal" and self.legal_mask is None:
+                raise ValueError("step(policy='legal') needs the 'legal_mask' output")
+            if forced_draws is not None:
+                raise ValueError("forced_draws and a policy cannot be combined")
+            pol = _lib.FLAG_POLICY_LEGAL if policy == "legal" else _lib.FLAG_POLICY_UNIFORM
+            if actions is None:
+                if self._actions_out is None:
+                    self._actions_out = torch.empty(n, dtype=torch.uint8, device=self.device)
+                act = self._actions_out
+            elif isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device \
+                    and actions.is_contiguous() and actions.shape == (n,):
+                act = actions
+            else:
+                raise ValueError("with a policy, actions is an OUTPUT: a contiguous uint8 [%d] tensor on %s" % (n, self.device))
+        elif isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == self.device \
                 and actions.is_contiguous() and actions.shape == (n,):
             act = actions                       # fast path: no validation pass over the batch
         else:
+            if actions is None:
+                raise ValueError("step() needs actions (or policy='uniform' / 'legal')")
             act = self._as_u8(actions, (n,), "actions")
         key = (self.seed, self.env_id_base, self.illegal_move_reward, self.max_tile_exp, self.auto_reset,
                None if self._step_counter is None else self._step_counter.data_ptr())
@@ -224,6 +251,7 @@ class BatchedGame2048:
         a.actions = act.data_ptr()
         a.step_index = self.step_index
         a.boards = self.boards.data_ptr()
+        a.flags = (FLAG_AUTO_RESET if self.auto_reset else 0) | pol
         a.boards_out = None if boards_out is None else self._check_board_buffer(boards_out, "boards_out").data_ptr()
         # every per-call pointer of the cached struct is reassigned on every call: a stale terminal_out would
         # keep the kernel writing into a buffer its owner (e.g. a dropped TransitionRecorder) may have freed
@@ -246,6 +274,7 @@ class BatchedGame2048:
             self.boards = boards_out
         res.boards = self.boards
         res.terminal_boards = terminal_out if terminal_out is not None else self.terminal_boards
+        res.actions = act
         return res
 
     def step_n(self, actions, rewards=None, dones=None, illegal=None, highest_exp=None, legal_mask_out=None):
@@ -509,40 +538,72 @@ class BatchedGame2048:
 class HostBuffers:
     """Pinned host arrays for HostSteppedEnv (numpy views over torch pinned memory)."""
 
-    def __init__(self, n, extras=False):
+    def __init__(self, n, extras=False, nibble=False):
         pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()       # noqa: E731
         self.actions = pin((n,), torch.uint8)
-        self.boards = pin((n, 16), torch.uint8)
+        self.boards = pin((n, 8 if nibble else 16), torch.uint8)
         self.rewards = pin((n,), torch.float32)
         self.dones = pin((n,), torch.uint8)
         self.illegal = pin((n,), torch.uint8) if extras else None
         self.highest_exp = pin((n,), torch.uint8) if extras else None
         self.legal_mask = pin((n,), torch.uint8) if extras else None
+        self.nibble = nibble
+        self.nibble_overflow = C.c_uint32(0)       # boards of the last step that did not fit 4 bits per cell
+
+    def unpacked_boards(self):
+        """uint8 [n,16] exponents from the compact format (cell c = nibble c of the 8 bytes), as a new tensor."""
+        if not self.nibble:
+            return self.boards
+        out = torch.empty((self.boards.shape[0], 16), dtype=torch.uint8)
+        out[:, 0::2] = self.boards & 15
+        out[:, 1::2] = self.boards >> 4
+        return out
 
 
 class HostSteppedEnv:
     """The stateful host-buffer handle of the C ABI (g2048_env_*): actions come from HOST
     memory and boards/rewards/dones land in HOST memory every step, with the host<->device
     copies chunk-pipelined against the kernel inside the library.  This is the call a
-    CPU-side caller (the reference's numpy world) makes; bench.py times it as `e2e`."""
+    CPU-side caller (the reference's numpy world) makes; bench.py times it as `e2e`.
+
+    board_format="nibble": the boards come back packed 4 bits per cell ([n,8] bytes, the classic 64-bit 2048
+    bitboard; cell c = nibble c) — the call is PCIe-bound and this cuts the bytes per board from 21 to 13.  A board
+    holding a tile >= 65,536 does not fit: `buffers.nibble_overflow.value` counts them per step and
+    full_boards() fetches the 16-byte boards."""
 
     def __init__(self, num_envs, seed=0, device=0, env_id_base=0, illegal_move_reward=0.0, max_tile=None,
-                 auto_reset=True, n_chunks=0, extras=False):
+                 auto_reset=True, n_chunks=0, extras=False, board_format="bytes"):
+        if board_format not in ("bytes", "nibble"):
+            raise ValueError("board_format must be 'bytes' or 'nibble'")
         self.lib = _lib.lib()
         self.num_envs = int(num_envs)
+        nibble = board_format == "nibble"
         cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
                              int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
-                             int(n_chunks), 0)
+                             int(n_chunks), _lib.BOARDS_NIBBLE if nibble else _lib.BOARDS_BYTES)
         self._n_chunks = min(int(n_chunks) if n_chunks else 3, 64)
         self._h = C.c_void_p()
         check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
-        self.buffers = HostBuffers(self.num_envs, extras)
+        self.buffers = HostBuffers(self.num_envs, extras, nibble)
         b = self.buffers
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())          # noqa: E731
         self._out = _lib.HostStepOut(p(b.boards), p(b.rewards), p(b.dones), p(b.illegal), p(b.highest_exp),
-                                     p(b.legal_mask))
+                                     p(b.legal_mask), C.cast(C.pointer(b.nibble_overflow), C.c_void_p))
+        self._full = None
+
+    def full_boards(self):
+        """The live boards as uint8 [n,16] exponents, whatever the board format (one synchronous D2H copy)."""
+        if self._full is None:
+            self._full = torch.empty((self.num_envs, 16), dtype=torch.uint8).pin_memory()
+        check(self.lib.g2048_env_get_boards_host(self._h, C.c_void_p(self._full.data_ptr())))
+        return self._full
 
     def reset(self):
+        """Fresh boards for every env; returns them as uint8 [n,16] exponents (also with board_format='nibble':
+        the compact format applies to step results)."""
+        if self.buffers.nibble:
+            check(self.lib.g2048_env_reset_host(self._h, None))
+            return self.full_boards()
         check(self.lib.g2048_env_reset_host(self._h, C.c_void_p(self.buffers.boards.data_ptr())))
         return self.buffers.boards
 
@@ -618,8 +679,21 @@ class StepSchedule:
     def __len__(self):
         return len(self._items)
 
-    def add(self, game, actions):
+    def add(self, game, actions=None, policy=None):
+        """Record game.step(actions) — or game.step(policy=...), the actions then being drawn by the kernel and written
+        to `actions` (or the game's internal buffer)."""
         n = game.num_envs
+        pol = 0
+        if policy is not None:
+            if policy not in ("uniform", "legal"):
+                raise ValueError("policy must be None, 'uniform' or 'legal'")
+            if policy == "legal" and game.legal_mask is None:
+                raise ValueError("policy='legal' needs the 'legal_mask' output")
+            pol = _lib.FLAG_POLICY_LEGAL if policy == "legal" else _lib.FLAG_POLICY_UNIFORM
+            if actions is None:
+                if game._actions_out is None:
+                    game._actions_out = torch.empty(n, dtype=torch.uint8, device=game.device)
+                actions = game._actions_out
         if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.device == game.device
                 and actions.is_contiguous() and actions.shape == (n,)):
             raise ValueError("actions must be a contiguous uint8 [%d] tensor on %s" % (n, game.device))
@@ -636,6 +710,7 @@ class StepSchedule:
         a.actions = actions.data_ptr()
         a.step_index = game.step_index
         a.boards = game.boards.data_ptr()
+        a.flags = (FLAG_AUTO_RESET if game.auto_reset else 0) | pol
         game.step_index += 1
         self._items.append(a)
         self._keep.append((game, actions))

@@ -154,6 +154,8 @@ struct StepParams {
   uint32_t* final_len;
   float* ep_return;
   float* final_return;
+  uint2* boards_nibble;         // [n] the board handed back, 4 bits per cell (cell c at bits 4c..4c+3 of the 64-bit word)
+  uint32_t* nibble_overflow;    // counter of boards whose exponents do not fit 4 bits (a tile >= 65,536)
   const uint4* forced_draws;
   uint64_t* step_counter;       // [0] step index, [1] CTA arrival ticket (0 between launches)
   uint32_t n;                   // < 2^32 - 256 (checked by the host)
@@ -161,6 +163,8 @@ struct StepParams {
   uint32_t env_hi;              // high half, the same for every board
   uint64_t seed;                // only read when step_counter is set (the key is then derived on the device)
   StreamKeys keys;              // Philox2x32 round keys of stream_key(seed, step_index, env_hi, TAG_STEP)
+  StreamKeys policy_keys;       // the same for TAG_POLICY (kernels that draw the actions themselves)
+  uint8_t* actions_out;         // POLICY kernels: where the drawn action goes (the caller's `actions` array)
   float illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t flags;
@@ -214,10 +218,11 @@ __device__ __forceinline__ uint4 load_board(const uint4* ptr) {
 //   0                                  lean: boards, actions, rewards, dones            (BASELINE configs 2, 3)
 //   O_MASK                             + legal mask                                     (BASELINE config 4)
 //   O_EPRUN                            + running episode score/length                   (g2048_env_step_host, `e2e`)
+//   O_EPRUN|O_NIBBLE                   + the board packed 4 bits per cell               (the same, compact host format)
 //   O_ILLEGAL|O_HIGHEST|O_MASK         the evaluator (train.py:122-214)
 //   kOutAll                            everything SB3's Monitor + DummyVecEnv report    (Game2048VecEnv)
 constexpr uint32_t O_ILLEGAL = 1u, O_HIGHEST = 2u, O_MASK = 4u, O_TERMINAL = 8u, O_EPRUN = 16u, O_EPFINAL = 32u,
-                   O_EPRET = 64u, O_FORCED = 128u, O_GENERIC = 0x80000000u;
+                   O_EPRET = 64u, O_FORCED = 128u, O_NIBBLE = 256u, O_GENERIC = 0x80000000u;
 constexpr uint32_t kOutEval = O_ILLEGAL | O_HIGHEST | O_MASK;
 constexpr uint32_t kOutAll = O_ILLEGAL | O_HIGHEST | O_MASK | O_TERMINAL | O_EPRUN | O_EPFINAL | O_EPRET;
 template <uint32_t OUT, uint32_t BIT> __device__ __forceinline__ bool has(const void* ptr) {
@@ -225,11 +230,26 @@ template <uint32_t OUT, uint32_t BIT> __device__ __forceinline__ bool has(const 
   else return (OUT & BIT) != 0u;
 }
 
+// The running episode statistics of a board, loaded AHEAD of the step (with the board, one loop iteration early):
+// read where they are used they cost an exposed HBM round trip per board (ncu: long-scoreboard stalls 0.7 -> 4.3
+// per issue cycle, 15 -> 17.8 us per 1 Mi boards for the O_EPRUN kernel).
+struct EpIn { uint32_t score, len; float ret; };
+template <uint32_t OUT>
+__device__ __forceinline__ EpIn load_episode(const StepParams& p, uint32_t i) {
+  EpIn e{0u, 0u, 0.f};
+  if constexpr (OUT != 0u) {
+    if (has<OUT, O_EPRUN>(p.ep_score)) e.score = p.ep_score[i];
+    if (has<OUT, O_EPRUN>(p.ep_len)) e.len = p.ep_len[i];
+    if (has<OUT, O_EPRET>(p.ep_return)) e.ret = p.ep_return[i];
+  }
+  return e;
+}
+
 // The finishing half of board i (spawn, score, isend, auto-reset) and its stores; `m` is what the
-// move half (move_oriented) left.
+// move half (move_oriented) left, `ep` the board's running episode statistics before the step.
 template <uint32_t OUT, bool COUNTER>
 __device__ __forceinline__ void finish_and_store(const StepParams& p, const Board4* lut, uint32_t i, const Moved& m,
-                                                 uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
+                                                 uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset, const EpIn ep) {
   Words w;
   if (has<OUT, O_FORCED>(p.forced_draws)) {
     const uint4 f = p.forced_draws[i];
@@ -254,9 +274,9 @@ __device__ __forceinline__ void finish_and_store(const StepParams& p, const Boar
     const bool h_er = has<OUT, O_EPRET>(p.ep_return);
     uint32_t es = 0, el = 0;
     float er = 0.f;
-    if (h_es) es = p.ep_score[i] + (uint32_t)o.score;                                    // :86
-    if (h_el) el = p.ep_len[i] + 1u;
-    if (h_er) er = p.ep_return[i] + reward;              // what SB3's Monitor sums: the rewards the agent saw
+    if (h_es) es = ep.score + (uint32_t)o.score;                                         // :86
+    if (h_el) el = ep.len + 1u;
+    if (h_er) er = ep.ret + reward;                      // what SB3's Monitor sums: the rewards the agent saw
     if (o.done) {
       if (has<OUT, O_TERMINAL>(p.terminal_boards)) p.terminal_boards[i] = make_uint4(o.t0, o.t1, o.t2, o.t3);
       if (has<OUT, O_EPFINAL>(p.final_score)) p.final_score[i] = es;
@@ -268,14 +288,24 @@ __device__ __forceinline__ void finish_and_store(const StepParams& p, const Boar
     if (h_el) p.ep_len[i] = el;
     if (h_er) p.ep_return[i] = er;
     if (has<OUT, O_MASK>(p.legal_mask)) p.legal_mask[i] = (uint8_t)legal_mask(bd.x, bd.y, bd.z, bd.w);
+    if (has<OUT, O_NIBBLE>(p.boards_nibble)) {
+      // 16 exponents -> 16 nibbles (the classic 64-bit 2048 board): per row, the low nibbles of the four bytes
+      auto pack_row = [](uint32_t r) {
+        uint32_t x = r & 0x0F0F0F0Fu;
+        x = (x | (x >> 4)) & 0x00FF00FFu;
+        return (x | (x >> 8)) & 0xFFFFu;
+      };
+      p.boards_nibble[i] = make_uint2(pack_row(bd.x) | (pack_row(bd.y) << 16), pack_row(bd.z) | (pack_row(bd.w) << 16));
+      if ((((bd.x | bd.y) | (bd.z | bd.w)) & 0xF0F0F0F0u) != 0u && p.nibble_overflow) atomicAdd(p.nibble_overflow, 1u);
+    }
   }
 }
 
 template <uint32_t OUT, bool COUNTER>
 __device__ __forceinline__ void step_and_store(const StepParams& p, const Board4* lut, uint32_t i, uint32_t a,
                                                uint32_t b, uint32_t c, uint32_t d, const Sel4 so,
-                                               uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset) {
-  finish_and_store<OUT, COUNTER>(p, lut, i, move_oriented(a, b, c, d, so), dev_key, dev_idx_lo, auto_reset);
+                                               uint32_t dev_key, uint32_t dev_idx_lo, bool auto_reset, const EpIn ep) {
+  finish_and_store<OUT, COUNTER>(p, lut, i, move_oriented(a, b, c, d, so), dev_key, dev_idx_lo, auto_reset, ep);
 }
 
 #ifndef G2048_PIPELINE       // 1: software-pipelined loop — the move half of board j+1 and the finishing half of
@@ -323,8 +353,14 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <uint32_t OUT, bool COUNTER>
+// POLICY 0: the actions are read from p.actions.  1 / 2: the kernel plays g2048_sample_actions' uniform / random-legal
+// policy itself — the action is drawn from the policy-tag stream at this step's index, for the legal policy among
+// the legal moves p.legal_mask holds for the board (the mask the previous step wrote) — and writes it to
+// p.actions_out: BASELINE config 4's "sample a legal action, step, return the new mask" is ONE launch.
+template <uint32_t OUT, bool COUNTER, int POLICY = 0>
 __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kernel(const StepParams p) {
+  static_assert(POLICY == 0 || (!G2048_TMA && !G2048_PIPELINE), "the policy kernels exist for the plain loop only");
+  static_assert(POLICY != 2 || (OUT & (O_MASK | O_GENERIC)) != 0u, "the random-legal policy reads and writes the legal mask");
 #if G2048_PAIR_LUT && !G2048_TMA
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
@@ -377,7 +413,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
   // requested while the previous launch drains: one lane per 128-byte line (8 boards), one per warp for the actions.
   if (i < n) {
     if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.boards + i));
-    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + i));
+    if (POLICY != 1 && (threadIdx.x & 31u) == 0u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"((POLICY == 2 ? p.legal_mask : p.actions) + i));
   }
 #endif
 #if G2048_PDL
@@ -388,10 +425,12 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
 #endif
   uint64_t counter_value = 0;
   uint32_t dev_key = 0u, dev_idx_lo = 0u;
+  [[maybe_unused]] uint32_t dev_policy_key = 0u;
   if (COUNTER) {                            // device-side step index (CUDA-graph replay)
     counter_value = p.step_counter[0];
     dev_key = stream_key(p.seed, counter_value, (uint64_t)p.env_hi << 32, TAG_STEP);
     dev_idx_lo = (uint32_t)counter_value;
+    if (POLICY) dev_policy_key = stream_key(p.seed, counter_value, (uint64_t)p.env_hi << 32, TAG_POLICY);
     __syncthreads();                        // every thread of the CTA has read the index before thread 0 can arrive
   }
 #if !G2048_TMA
@@ -451,7 +490,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     uint32_t a, b, c, d;
     orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
     const Sel4 so = s_sel[4u + act];
-    if (valid) step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
+    if (valid) step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset, load_episode<OUT>(p, i));
     if (++stage == (uint32_t)kStages) { stage = 0; parity ^= 1u; }
     if (++fill_stage == (uint32_t)kStages) { fill_stage = 0; fill_parity ^= 1u; }
   }
@@ -485,18 +524,21 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
       const Sel4 so = s_sel[4u + act];
       if (more_next) { bd = load_board(p.boards + i_next); action = p.actions[i_next]; }
       const Moved m_next = move_oriented(a, b, c, d, so);
-      finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
+      finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset, load_episode<OUT>(p, i));
       m = m_next;
       i = i_cur;
       more = more_next;
     }
-    finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset);
+    finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset, load_episode<OUT>(p, i));
   }
 #else
   const uint4* pb = p.boards + i;
-  const uint8_t* pa = p.actions + i;
+  // the byte prefetched next to the board: the action, or (random-legal policy) the board's legal mask
+  const uint8_t* const side = POLICY == 2 ? p.legal_mask : p.actions;
+  const uint8_t* pa = side + i;
   uint4 bd = load_board(pb);
-  uint32_t action = *pa;
+  uint32_t action = POLICY == 1 ? 15u : *pa;
+  EpIn ep_next = load_episode<OUT>(p, i);
 #if G2048_STAGGER
   // Experiment: the eight warps of an SM sub-partition run the same instruction stream in near lockstep — all in
   // the ALU-heavy move, then all in the FMA-heavy Philox/spawn — so the two pipes take turns idling.  Start them
@@ -506,7 +548,15 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
   while (true) {
     const uint32_t i_next = i + stride;
     const bool more = G2048_PERSISTENT && i_next < n && i_next > i;
-    const uint32_t act = action & 3u;
+    uint32_t act;
+    if (POLICY) {
+      const Pair pw = COUNTER ? philox2x32_10(p.env_lo + i, dev_idx_lo, dev_policy_key)
+                              : philox2x32_10_keys(p.env_lo + i, p.policy_keys);
+      act = pick_action(action, pw.x0);
+      p.actions_out[i] = (uint8_t)act;
+    } else {
+      act = action & 3u;
+    }
     uint32_t a, b, c, d;
 #if G2048_SEL_SMEM
     orient(s_sel[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
@@ -515,20 +565,26 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     orient(kOrientIn[act], bd.x, bd.y, bd.z, bd.w, a, b, c, d);
     const Sel4 so = kOrientOut[act];
 #endif
+    const EpIn ep = ep_next;
 #if G2048_PREFETCH
     if (more) {
+      ep_next = load_episode<OUT>(p, i_next);
 #if G2048_PTR_INC
       pb += stride; pa += stride;
-      bd = load_board(pb); action = *pa;
+      bd = load_board(pb);
+      if (POLICY != 1) action = *pa;
 #else
-      bd = load_board(p.boards + i_next); action = p.actions[i_next];
+      bd = load_board(p.boards + i_next);
+      if (POLICY != 1) action = side[i_next];
 #endif
     }
 #endif
-    step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset);
+    step_and_store<OUT, COUNTER>(p, lut, i, a, b, c, d, so, dev_key, dev_idx_lo, auto_reset, ep);
     if (!more) break;
 #if !G2048_PREFETCH
-    bd = load_board(p.boards + i_next); action = p.actions[i_next];
+    bd = load_board(p.boards + i_next);
+    if (POLICY != 1) action = side[i_next];
+    ep_next = load_episode<OUT>(p, i_next);
 #endif
     i = i_next;
   }
@@ -971,6 +1027,9 @@ struct G2048Env {
   uint8_t* d_mask;
   uint32_t* d_ep_score;
   uint32_t* d_ep_len;
+  uint8_t* d_nibble;            // [n*8] compact host format (cfg.board_format == G2048_BOARDS_NIBBLE)
+  uint32_t* d_overflow;         // [64] per-slice counters of boards that do not fit the compact format
+  uint32_t* h_overflow;         // pinned mirror of d_overflow
   cudaStream_t streams[4];
   int n_streams;
 };
@@ -989,7 +1048,7 @@ static G2048StepArgs slice_args(const G2048StepArgs& a, uint64_t lo, uint64_t m)
   adv(s.boards, 16); adv(s.boards_out, 16); adv(s.actions, 1); adv(s.rewards, 1); adv(s.dones, 1);
   adv(s.illegal, 1); adv(s.highest_exp, 1); adv(s.legal_mask, 1); adv(s.terminal_boards, 16);
   adv(s.ep_score, 1); adv(s.ep_len, 1); adv(s.final_score, 1); adv(s.final_len, 1); adv(s.forced_draws, 4);
-  adv(s.ep_return, 1); adv(s.final_return, 1);
+  adv(s.ep_return, 1); adv(s.final_return, 1); adv(s.boards_nibble, 8);
   s.n = m;
   s.env_id_base = a.env_id_base + lo;
   return s;
@@ -997,17 +1056,28 @@ static G2048StepArgs slice_args(const G2048StepArgs& a, uint64_t lo, uint64_t m)
 
 // The step kernels the library instantiates: (output set, device-side step counter) -> kernel.  Any other
 // combination of optional pointers runs the generic kernel.
-struct StepKernelEntry { uint32_t out; bool counter; const void* fn; };
+struct StepKernelEntry { uint32_t out; bool counter; int policy; const void* fn; };
 static const StepKernelEntry kStepKernels[] = {
-    {0u, false, (const void*)g2048_step_kernel<0u, false>},
-    {0u, true, (const void*)g2048_step_kernel<0u, true>},
-    {O_MASK, false, (const void*)g2048_step_kernel<O_MASK, false>},
-    {O_MASK, true, (const void*)g2048_step_kernel<O_MASK, true>},
-    {O_EPRUN, false, (const void*)g2048_step_kernel<O_EPRUN, false>},
-    {kOutEval, false, (const void*)g2048_step_kernel<kOutEval, false>},
-    {kOutAll, false, (const void*)g2048_step_kernel<kOutAll, false>},
-    {O_GENERIC, false, (const void*)g2048_step_kernel<O_GENERIC, false>},
-    {O_GENERIC, true, (const void*)g2048_step_kernel<O_GENERIC, true>},
+    {0u, false, 0, (const void*)g2048_step_kernel<0u, false>},
+    {0u, true, 0, (const void*)g2048_step_kernel<0u, true>},
+    {O_MASK, false, 0, (const void*)g2048_step_kernel<O_MASK, false>},
+    {O_MASK, true, 0, (const void*)g2048_step_kernel<O_MASK, true>},
+    {O_EPRUN, false, 0, (const void*)g2048_step_kernel<O_EPRUN, false>},
+    {O_EPRUN | O_NIBBLE, false, 0, (const void*)g2048_step_kernel<O_EPRUN | O_NIBBLE, false>},
+    {kOutEval, false, 0, (const void*)g2048_step_kernel<kOutEval, false>},
+    {kOutAll, false, 0, (const void*)g2048_step_kernel<kOutAll, false>},
+    {O_GENERIC, false, 0, (const void*)g2048_step_kernel<O_GENERIC, false>},
+    {O_GENERIC, true, 0, (const void*)g2048_step_kernel<O_GENERIC, true>},
+#if !G2048_TMA && !G2048_PIPELINE
+    // the kernel draws the actions itself (G2048_FLAG_POLICY_UNIFORM / _LEGAL)
+    {0u, false, 1, (const void*)g2048_step_kernel<0u, false, 1>},
+    {O_MASK, false, 2, (const void*)g2048_step_kernel<O_MASK, false, 2>},
+    {O_MASK, true, 2, (const void*)g2048_step_kernel<O_MASK, true, 2>},
+    {O_GENERIC, false, 1, (const void*)g2048_step_kernel<O_GENERIC, false, 1>},
+    {O_GENERIC, false, 2, (const void*)g2048_step_kernel<O_GENERIC, false, 2>},
+    {O_GENERIC, true, 1, (const void*)g2048_step_kernel<O_GENERIC, true, 1>},
+    {O_GENERIC, true, 2, (const void*)g2048_step_kernel<O_GENERIC, true, 2>},
+#endif
 };
 // The optional pointers of a call as an output set; *exact = false when a pointer group is only partly given
 // (the specialised kernels write whole groups).
@@ -1019,6 +1089,7 @@ static uint32_t output_set(const G2048StepArgs* a, bool* exact) {
   if (a->legal_mask) have |= O_MASK;
   if (a->terminal_boards) have |= O_TERMINAL;
   if (a->forced_draws) have |= O_FORCED;
+  if (a->boards_nibble) have |= O_NIBBLE;
   auto group = [&](const void* x, const void* y, uint32_t bit) {
     if (x && y) have |= bit;
     else if (x || y) { have |= bit; *exact = false; }
@@ -1032,9 +1103,10 @@ static const void* pick_step_kernel(const G2048StepArgs* a) {
   bool exact = true;
   const uint32_t have = output_set(a, &exact);
   const bool counter = a->step_counter != nullptr;
+  const int policy = (a->flags & G2048_FLAG_POLICY_LEGAL) ? 2 : (a->flags & G2048_FLAG_POLICY_UNIFORM) ? 1 : 0;
   const void* generic = nullptr;
   for (const StepKernelEntry& e : kStepKernels) {
-    if (e.counter != counter) continue;
+    if (e.counter != counter || e.policy != policy) continue;
     if (exact && e.out == have) return e.fn;
     if (e.out == O_GENERIC) generic = e.fn;
   }
@@ -1042,6 +1114,7 @@ static const void* pick_step_kernel(const G2048StepArgs* a) {
 }
 
 static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepParams& p) {
+  std::memset(&p, 0, sizeof p);
   p.boards = reinterpret_cast<const uint4*>(a->boards);
   p.boards_out = reinterpret_cast<uint4*>(a->boards_out ? a->boards_out : a->boards);
   p.actions = a->actions;
@@ -1057,6 +1130,8 @@ static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepPara
   p.final_len = a->final_len;
   p.ep_return = a->ep_return;
   p.final_return = a->final_return;
+  p.boards_nibble = reinterpret_cast<uint2*>(a->boards_nibble);
+  p.nibble_overflow = a->nibble_overflow;
   p.forced_draws = reinterpret_cast<const uint4*>(a->forced_draws);
   p.step_counter = a->step_counter;
   p.n = (uint32_t)a->n;
@@ -1064,6 +1139,9 @@ static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepPara
   p.env_hi = (uint32_t)(a->env_id_base >> 32);
   p.seed = a->seed;
   make_stream_keys(stream_key(a->seed, a->step_index, a->env_id_base, TAG_STEP), (uint32_t)a->step_index, p.keys);
+  if (a->flags & (G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL))
+    make_stream_keys(stream_key(a->seed, a->step_index, a->env_id_base, TAG_POLICY), (uint32_t)a->step_index, p.policy_keys);
+  p.actions_out = const_cast<uint8_t*>(a->actions);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = (a->flags & ~kFlagBumpCounter) | (bump_counter ? kFlagBumpCounter : 0u);
@@ -1120,7 +1198,9 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   cudaLaunchAttribute attr[1];
   step_launch_config(a->n, s, cfg, attr);
   void* kargs[] = {&p};
-  const cudaError_t le = cudaLaunchKernelExC(&cfg, pick_step_kernel(a), kargs);
+  const void* kernel = pick_step_kernel(a);
+  if (!kernel) return fail(G2048_ERR_INVALID, "g2048_step: this build has no kernel for the requested policy flag");
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, kernel, kargs);
   if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(g2048_step_kernel)");
   return G2048_OK;
 }
@@ -1133,9 +1213,17 @@ static int check_step_args(const G2048StepArgs* a, const char* fn) {
   if (!aligned16(a->boards) || !aligned16(a->boards_out) || !aligned16(a->terminal_boards) ||
       !aligned16(a->forced_draws))
     return fail(G2048_ERR_ALIGN, "%s: boards / boards_out / terminal_boards / forced_draws must be 16-byte aligned", fn);
+  if (reinterpret_cast<uintptr_t>(a->boards_nibble) & 7u)
+    return fail(G2048_ERR_ALIGN, "%s: boards_nibble must be 8-byte aligned", fn);
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "%s: max_tile_exp %u > 63", fn, a->max_tile_exp);
-  if (a->flags & ~G2048_FLAG_AUTO_RESET)
-    return fail(G2048_ERR_INVALID, "%s: unknown flags 0x%x (the policy flags belong to g2048_step_many)", fn, a->flags);
+  if (a->flags & ~(G2048_FLAG_AUTO_RESET | G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL))
+    return fail(G2048_ERR_INVALID, "%s: unknown flags 0x%x", fn, a->flags);
+  if ((a->flags & G2048_FLAG_POLICY_UNIFORM) && (a->flags & G2048_FLAG_POLICY_LEGAL))
+    return fail(G2048_ERR_INVALID, "%s: choose one of G2048_FLAG_POLICY_UNIFORM / G2048_FLAG_POLICY_LEGAL", fn);
+  if ((a->flags & G2048_FLAG_POLICY_LEGAL) && !a->legal_mask)
+    return fail(G2048_ERR_INVALID, "%s: G2048_FLAG_POLICY_LEGAL draws among the moves in legal_mask, which is NULL", fn);
+  if ((a->flags & (G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL)) && a->forced_draws)
+    return fail(G2048_ERR_INVALID, "%s: forced_draws and a policy flag cannot be combined", fn);
   if (a->n > 0xFFFFFF00ull) return fail(G2048_ERR_INVALID, "%s: n must be < 2^32 - 256 per call", fn);
   return G2048_OK;
 }
@@ -1186,6 +1274,7 @@ int g2048_step_n(const G2048StepArgs* a, uint32_t n_steps, uint64_t row_stride, 
     if (k.final_len) k.final_len += row_stride;
     if (k.final_return) k.final_return += row_stride;
     if (k.forced_draws) k.forced_draws += 4 * row_stride;
+    if (k.boards_nibble) k.boards_nibble += 8 * row_stride;
     k.step_index += 1;
   }
   return launch_check("g2048_step_kernel");
@@ -1456,7 +1545,8 @@ int g2048_env_destroy(G2048Env* e) {
   for (int i = 0; i < e->n_streams; ++i) cudaStreamDestroy(e->streams[i]);
   cudaFree(e->d_boards); cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_dones);
   cudaFree(e->d_illegal); cudaFree(e->d_highest); cudaFree(e->d_mask);
-  cudaFree(e->d_ep_score); cudaFree(e->d_ep_len);
+  cudaFree(e->d_ep_score); cudaFree(e->d_ep_len); cudaFree(e->d_nibble); cudaFree(e->d_overflow);
+  if (e->h_overflow) cudaFreeHost(e->h_overflow);
   delete e;
   return G2048_OK;
 }
@@ -1465,6 +1555,7 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   if (!out || !cfg) return fail(G2048_ERR_INVALID, "g2048_env_create: NULL argument");
   if (cfg->n == 0) return fail(G2048_ERR_INVALID, "g2048_env_create: n must be > 0");
   if (cfg->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_env_create: max_tile_exp > 63");
+  if (cfg->board_format > G2048_BOARDS_NIBBLE) return fail(G2048_ERR_INVALID, "g2048_env_create: unknown board_format %u", cfg->board_format);
   G2048_CUDA(cudaSetDevice(cfg->device));
   G2048Env* e = new (std::nothrow) G2048Env();
   if (!e) return fail(G2048_ERR_NOMEM, "g2048_env_create: out of host memory");
@@ -1478,6 +1569,10 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   alloc((void**)&e->d_boards, n * 16); alloc((void**)&e->d_actions, n); alloc((void**)&e->d_rewards, n * 4);
   alloc((void**)&e->d_dones, n); alloc((void**)&e->d_illegal, n); alloc((void**)&e->d_highest, n);
   alloc((void**)&e->d_mask, n); alloc((void**)&e->d_ep_score, n * 4); alloc((void**)&e->d_ep_len, n * 4);
+  if (cfg->board_format == G2048_BOARDS_NIBBLE) {
+    alloc((void**)&e->d_nibble, n * 8); alloc((void**)&e->d_overflow, 64 * 4);
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_overflow, 64 * 4, cudaHostAllocDefault);
+  }
   if (err == cudaSuccess) err = cudaMemset(e->d_ep_score, 0, n * 4);
   if (err == cudaSuccess) err = cudaMemset(e->d_ep_len, 0, n * 4);
   if (err == cudaSuccess) err = cudaMemset(e->d_boards, 0, n * 16);
@@ -1543,8 +1638,10 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   const uint64_t rest_chunks = lead ? e->n_chunks - 1 : e->n_chunks;
   uint64_t per = (n - lead + rest_chunks - 1) / rest_chunks;
   per = (per + 255) / 256 * 256;
+  const bool nibble = e->cfg.board_format == G2048_BOARDS_NIBBLE;
   // One slice: H2D(actions) -> step kernel -> D2H(results), all on stream s.
-  auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s) -> int {
+  auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s, int c) -> int {
+    if (nibble) G2048_CUDA(cudaMemsetAsync(e->d_overflow + c, 0, 4, s));
     G2048_CUDA(cudaMemcpyAsync(e->d_actions + lo, actions_host + lo, m, cudaMemcpyHostToDevice, s));
     G2048StepArgs a;
     std::memset(&a, 0, sizeof a);
@@ -1557,6 +1654,7 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     a.legal_mask = o->legal_mask ? e->d_mask + lo : nullptr;
     a.ep_score = e->d_ep_score + lo;
     a.ep_len = e->d_ep_len + lo;
+    if (nibble) { a.boards_nibble = e->d_nibble + 8 * lo; a.nibble_overflow = e->d_overflow + c; }
     a.n = m;
     a.env_id_base = e->cfg.env_id_base + lo;
     a.seed = e->cfg.seed;
@@ -1566,7 +1664,12 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     a.flags = e->cfg.flags;
     const int rc = g2048_step(&a, s);
     if (rc) return rc;
-    G2048_CUDA(cudaMemcpyAsync(o->boards + 16 * lo, e->d_boards + 16 * lo, 16 * m, cudaMemcpyDeviceToHost, s));
+    if (nibble) {
+      G2048_CUDA(cudaMemcpyAsync(o->boards + 8 * lo, e->d_nibble + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, s));
+      G2048_CUDA(cudaMemcpyAsync(e->h_overflow + c, e->d_overflow + c, 4, cudaMemcpyDeviceToHost, s));
+    } else {
+      G2048_CUDA(cudaMemcpyAsync(o->boards + 16 * lo, e->d_boards + 16 * lo, 16 * m, cudaMemcpyDeviceToHost, s));
+    }
     G2048_CUDA(cudaMemcpyAsync(o->rewards + lo, e->d_rewards + lo, 4 * m, cudaMemcpyDeviceToHost, s));
     G2048_CUDA(cudaMemcpyAsync(o->dones + lo, e->d_dones + lo, m, cudaMemcpyDeviceToHost, s));
     if (o->illegal) G2048_CUDA(cudaMemcpyAsync(o->illegal + lo, e->d_illegal + lo, m, cudaMemcpyDeviceToHost, s));
@@ -1578,7 +1681,7 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   for (uint64_t lo = 0; lo < n; ++c) {
     const uint64_t want = (c == 0 && lead) ? lead : per;
     const uint64_t m = (n - lo < want) ? n - lo : want;
-    const int rc = issue_slice(lo, m, e->streams[c % e->n_streams]);
+    const int rc = issue_slice(lo, m, e->streams[c % e->n_streams], c);
     if (rc) {
       // Some slices of this step may already have run.  Drain the streams (no work of the failed call is left
       // in flight over the caller's host buffers) and say that the env is no longer at a step boundary: the
@@ -1593,7 +1696,21 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     lo += m;
   }
   e->step_index += 1;
-  return env_sync(e);
+  const int rc = env_sync(e);
+  if (rc == G2048_OK && nibble && o->nibble_overflow) {
+    uint32_t total = 0;
+    for (int k = 0; k < c; ++k) total += e->h_overflow[k];
+    *o->nibble_overflow = total;
+  }
+  return rc;
+}
+
+int g2048_env_get_boards_host(G2048Env* e, uint8_t* boards_host) {
+  if (!e || !boards_host) return fail(G2048_ERR_INVALID, "g2048_env_get_boards_host: NULL argument");
+  G2048_CUDA(cudaSetDevice(e->cfg.device));
+  G2048_CUDA(cudaMemcpyAsync(boards_host, e->d_boards, e->cfg.n * 16, cudaMemcpyDeviceToHost, e->streams[0]));
+  G2048_CUDA(cudaStreamSynchronize(e->streams[0]));
+  return G2048_OK;
 }
 
 int g2048_env_device_ptrs(G2048Env* e, uint8_t** boards, float** rewards, uint8_t** dones) {

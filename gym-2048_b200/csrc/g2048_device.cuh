@@ -27,6 +27,14 @@
 #define G2048_HD_CONSTEXPR __host__ __device__ constexpr      // also evaluated at compile time (the fresh-board table)
 #endif
 
+// EXPERIMENTS ONLY (scripts/kernel_variants.py): a bit mask that REMOVES parts of the step so that their marginal
+// cost can be measured in place.  Any non-zero value computes wrong results; the product is built with 0.
+//   1 Philox without wide multiplies   2 no tile insertion   8 no score   16 no Philox   32 no spawn
+//   64 no merge   128 no compaction + merge   256 no orientation networks
+#ifndef G2048_ABLATE
+#define G2048_ABLATE 0
+#endif
+
 namespace g2048 {
 
 constexpr uint32_t H = 0x80808080u;   // bit 7 of every byte
@@ -50,6 +58,9 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline uint32_t __popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) {         // shf.r.clamp: shift count min(sh, 32)
+  return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh > 32u ? 32u : sh));
+}
 #else
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
@@ -68,13 +79,20 @@ template <int S> inline uint32_t shl(uint32_t x) { return x << S; }
 inline uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
 #else
 static __constant__ uint32_t kOne = 1u;
+#ifndef G2048_ADDF_PLAIN      // 1: addf() is a plain add (ptxas picks IADD3 / IMAD itself) — experiment
+#define G2048_ADDF_PLAIN 1
+#endif
 __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
+#if G2048_ADDF_PLAIN
+  return x + y;
+#else
   uint32_t d;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(kOne), "r"(y));
   return d;
+#endif
 }
 #ifndef G2048_SHR_ALU         // 1: constant right shifts as SHF (ALU pipe) instead of IMAD.HI (FMA-heavy, quarter rate)
-#define G2048_SHR_ALU 0
+#define G2048_SHR_ALU 1
 #endif
 template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) {
   return G2048_SHR_ALU ? (x >> S) : __umulhi(x, 1u << (32 - S));
@@ -167,6 +185,18 @@ G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, uint32_t k0, const StreamKeys
   return Pair{c0, c1};
 }
 G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, const StreamKeys& ks) {
+#if G2048_ABLATE & 16
+  return Pair{env_lo * 0x9E3779B9u ^ ks.k[0], env_lo * 0x85EBCA6Bu ^ ks.k[1]};
+#elif G2048_ABLATE & 1
+  uint32_t c0 = (0x85EBCA6Bu * env_lo) ^ ks.k[0], c1 = PHILOX2_M * env_lo;
+#pragma unroll
+  for (int r = 1; r < 10; ++r) {
+    const uint32_t hi = 0x85EBCA6Bu * c0, lo = PHILOX2_M * c0;
+    c0 = hi ^ ks.k[r] ^ c1;
+    c1 = lo;
+  }
+  return Pair{c0, c1};
+#else
   uint32_t c0 = mulhi32(PHILOX2_M, env_lo) ^ ks.k[0], c1 = PHILOX2_M * env_lo;
 #pragma unroll
   for (int r = 1; r < 10; ++r) {
@@ -175,6 +205,7 @@ G2048_DEV Pair philox2x32_10_keys(uint32_t env_lo, const StreamKeys& ks) {
     c1 = lo;
   }
   return Pair{c0, c1};
+#endif
 }
 
 // Draw words from the generator output: w0 = x0 spawns after a legal move; a reset spawns with
@@ -234,12 +265,16 @@ G2048_CONST Sel4 kOrientOut[4] = {
 
 G2048_DEV void orient(const Sel4 s, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3,
                                        uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+#if G2048_ABLATE & 256
+  a = r0 ^ s.A; b = r1; c = r2; d = r3;
+#else
   const uint32_t x0 = prmt(r0, r2, s.A), x1 = prmt(r0, r2, s.B);
   const uint32_t y0 = prmt(r1, r3, s.A), y1 = prmt(r1, r3, s.B);
   a = prmt(x0, y0, s.C);
   b = prmt(x0, y0, s.D);
   c = prmt(x1, y1, s.C);
   d = prmt(x1, y1, s.D);
+#endif
 }
 
 // ---- shift (:243-260) on four lines at once -----------------------------------------
@@ -294,14 +329,25 @@ G2048_DEV float biased_sum(uint32_t biased) {
 }
 // The move score (:254) from the two biased slot words of slide_merge_slots: an exact float (a sum
 // of at most 8 powers of two <= 2^18).
-G2048_DEV float slots_score(uint32_t biased_a, uint32_t biased_b) { return biased_sum(biased_a) + biased_sum(biased_b); }
+G2048_DEV float slots_score(uint32_t biased_a, uint32_t biased_b) {
+#if G2048_ABLATE & 8
+  return (float)((biased_a ^ biased_b) & 0xFFu);
+#endif
+  return biased_sum(biased_a) + biased_sum(biased_b);
+}
 
 // Slide (a,b,c,d) toward a with merging.  The merged tiles come back as two biased slot words
 // (slots_score turns them into the move score): the step kernel carries those two registers from
 // the move half of one board into the finishing half, which runs an iteration later.
 G2048_DEV void slide_merge_slots(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, uint32_t& biased_a,
                                  uint32_t& biased_b) {
+#if G2048_ABLATE & 128
+  biased_a = a & 0x7F; biased_b = b & 0x7F; a ^= d; return;
+#endif
   compact(a, b, c, d);
+#if G2048_ABLATE & 64
+  biased_a = a & 0x7F; biased_b = b & 0x7F; return;
+#endif
   // merges on the compacted line: leftmost pair first, each tile merges once (:252-259)
   //   m1: a==b!=0;  m2: b==c!=0 and not m1;  m3: c==d!=0 and not m2   (bit 7 of each byte)
   const uint32_t m1 = ~addf(a ^ b, L7) & addf(b, L7);
@@ -370,6 +416,9 @@ __device__ __forceinline__ uint32_t insert_tile(uint32_t t, uint32_t mult, uint3
 #endif
 G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t w,
                          uint32_t enable = 0xFFFFFFFFu) {
+#if G2048_ABLATE & 32
+  r0 ^= w & enable & 1u; return 2u + (w & 3u);
+#endif
   // e_i: bit 7 set where the cell is empty; q_i: 0/1 per byte
   const uint32_t e0 = ~sp_add(r0, L7) & H, e1 = ~sp_add(r1, L7) & H, e2 = ~sp_add(r2, L7) & H, e3 = ~sp_add(r3, L7) & H;
   const uint32_t q0 = sp_shr<7>(e0), q1 = sp_shr<7>(e1), q2 = sp_shr<7>(e2), q3 = sp_shr<7>(e3);
@@ -389,7 +438,18 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
   // (tile 2, exponent 1) or 6 (tile 4, exponent 2) gives the tile byte; the cell is empty, so adding
   // equals inserting.  The shift is the high half of t_i * 2^25 / 2^26: one IMAD.HI per row, and a
   // zero multiplier (illegal move: no tile, :91-95) disables the spawn.
-#if defined(G2048_SPREAD_INSERT) && G2048_SPREAD_INSERT
+#ifndef G2048_SHIFT_INSERT
+#define G2048_SHIFT_INSERT 1
+#endif
+#if G2048_SHIFT_INSERT
+  // the flag (bit 7 of the target byte) shifted down to the tile's exponent: >> 7 for a 2, >> 6 for a 4; a shift
+  // count of 32 (funnel shift of a zero upper word) drops the flag: no tile after an illegal move (:91-95)
+  const uint32_t sh = enable ? ((f < P2_THRESHOLD) ? 7u : 6u) : 32u;                              // :168
+  r0 += __funnelshift_rc(sp_add(p0, gk) & ~sp_add(p0, gk1) & e0, 0u, sh);
+  r1 += __funnelshift_rc(sp_add(p1, gk) & ~sp_add(p1, gk1) & e1, 0u, sh);
+  r2 += __funnelshift_rc(sp_add(p2, gk) & ~sp_add(p2, gk1) & e2, 0u, sh);
+  r3 += __funnelshift_rc(sp_add(p3, gk) & ~sp_add(p3, gk1) & e3, 0u, sh);
+#elif defined(G2048_SPREAD_INSERT) && G2048_SPREAD_INSERT
   const uint32_t tile = ((f < P2_THRESHOLD) ? K1 : 2u * K1) & enable;                             // :168
   r0 |= spread(sp_add(p0, gk) & ~sp_add(p0, gk1) & e0) & tile;
   r1 |= spread(sp_add(p1, gk) & ~sp_add(p1, gk1) & e1) & tile;
@@ -397,6 +457,11 @@ G2048_DEV uint32_t spawn(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
   r3 |= spread(sp_add(p3, gk) & ~sp_add(p3, gk1) & e3) & tile;
 #else
   const uint32_t mult = ((f < P2_THRESHOLD) ? (1u << 25) : (1u << 26)) & enable;                  // :168
+#if G2048_ABLATE & 2
+  r0 ^= (sp_add(p0, gk) & ~sp_add(p0, gk1) & e0) ^ (sp_add(p1, gk) & ~sp_add(p1, gk1) & e1) ^ (sp_add(p2, gk) & ~sp_add(p2, gk1) & e2) ^
+        (sp_add(p3, gk) & ~sp_add(p3, gk1) & e3) ^ mult;
+  return n;
+#endif
   r0 = insert_tile(sp_add(p0, gk) & ~sp_add(p0, gk1) & e0, mult, r0);
   r1 = insert_tile(sp_add(p1, gk) & ~sp_add(p1, gk1) & e1, mult, r1);
   r2 = insert_tile(sp_add(p2, gk) & ~sp_add(p2, gk1) & e2, mult, r2);
@@ -520,12 +585,25 @@ G2048_DEV void board_rot1(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3
 // ---- random policies (train.py:119 random.randint(0, 3); random-legal of BASELINE config 4) ---
 // The k-th set bit of the 4-bit mask of allowed actions (all four when the mask is empty),
 // k = hi32(w * popcount): uniform over the allowed set.
+// Branch-free: the index of the k-th set bit of every 4-bit mask comes from a 16-byte table (byte m holds the four
+// 2-bit answers for k = 0..3), read with two PRMTs.
+G2048_HD_CONSTEXPR uint32_t kth_bit_byte(uint32_t m) {
+  uint32_t out = 0, k = 0;
+  for (uint32_t b = 0; b < 4; ++b)
+    if (m & (1u << b)) out |= b << (2u * k++);
+  return out;
+}
+G2048_HD_CONSTEXPR uint32_t kth_bit_word(uint32_t m0) {
+  return kth_bit_byte(m0) | (kth_bit_byte(m0 + 1) << 8) | (kth_bit_byte(m0 + 2) << 16) | (kth_bit_byte(m0 + 3) << 24);
+}
 G2048_DEV uint32_t pick_action(uint32_t mask, uint32_t w) {
   uint32_t m = mask & 15u;
   if (m == 0u) m = 15u;
-  uint32_t k = __umulhi(w, __popc(m));
-  for (; k > 0u; --k) m &= m - 1u;       // drop the k lowest allowed actions
-  return __popc((m & (0u - m)) - 1u);    // index of the lowest remaining one
+  const uint32_t k = __umulhi(w, __popc(m));
+  constexpr uint32_t T0 = kth_bit_word(0), T1 = kth_bit_word(4), T2 = kth_bit_word(8), T3 = kth_bit_word(12);
+  const uint32_t lo = prmt(T0, T1, m & 7u), hi = prmt(T2, T3, m & 7u);      // byte 0 = table[m & 7] / table[8 + (m & 7)]
+  const uint32_t byte = (m & 8u) ? hi : lo;
+  return (byte >> (2u * k)) & 3u;
 }
 
 // ---- one whole step (:76-100) on a board held in registers --------------------------

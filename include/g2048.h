@@ -71,7 +71,8 @@ extern "C" {
 /* G2048StepArgs.flags */
 #define G2048_FLAG_AUTO_RESET 1u /* SB3 DummyVecEnv semantics: a terminated env is   */
                                  /* replaced by a fresh reset() board in the same step */
-/* g2048_step_many only: the kernel plays g2048_sample_actions' policy itself */
+/* g2048_step / _step_n / _step_list / _step_many: the kernel plays g2048_sample_actions'    */
+/* policy itself and WRITES the action it drew (g2048_step: into `actions`)                */
 #define G2048_FLAG_POLICY_UNIFORM 2u /* action uniform in {0,1,2,3} (train.py:119)        */
 #define G2048_FLAG_POLICY_LEGAL   4u /* uniform among the legal moves of the live board   */
 
@@ -90,7 +91,15 @@ extern "C" {
  */
 typedef struct G2048StepArgs {
   uint8_t*        boards;          /* [n*16] in/out (in only when boards_out is set)       */
-  const uint8_t*  actions;         /* [n]    0..3; only the low 2 bits are read            */
+  const uint8_t*  actions;         /* [n]    0..3; only the low 2 bits are read.  With a   */
+                                   /*        G2048_FLAG_POLICY_* flag this array is an     */
+                                   /*        OUTPUT: the kernel draws the action exactly as */
+                                   /*        g2048_sample_actions(legal_mask or NULL, ...,  */
+                                   /*        step_index) would and stores it here; _LEGAL   */
+                                   /*        needs legal_mask, which then is in (the mask   */
+                                   /*        of the board being stepped) AND out (the mask  */
+                                   /*        of the board handed back): BASELINE config 4   */
+                                   /*        as one launch per step                         */
   float*          rewards;         /* [n]    out: merge score, or illegal_move_reward      */
   uint8_t*        dones;           /* [n]    out: terminated (0/1)                         */
   uint8_t*        illegal;         /* [n]    out, nullable: info['illegal_move']           */
@@ -125,6 +134,13 @@ typedef struct G2048StepArgs {
                                    /*        the step emitted (illegal_move_reward included */
                                    /*        — what SB3's Monitor sums, ppo_train.py:123)   */
   float*          final_return;    /* [n]    out, nullable: that sum, where done           */
+  uint8_t*        boards_nibble;   /* [n*8]  out, nullable: the board handed back, packed  */
+                                   /*        4 bits per cell — cell c = bits 4c..4c+3 of   */
+                                   /*        the little-endian 64-bit word, the classic    */
+                                   /*        2048 bitboard; holds exponents <= 15 (tiles   */
+                                   /*        <= 32768); 8-byte aligned                     */
+  uint32_t*       nibble_overflow; /* device uint32, nullable: incremented once per board  */
+                                   /*        whose exponents do not fit (a tile >= 65536)  */
 } G2048StepArgs;
 
 int g2048_abi_version(void);
@@ -402,17 +418,26 @@ typedef struct G2048EnvConfig {
   float    illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default (3: a 1/16 lead slice + 2) */
-  uint32_t reserved;
+  uint32_t board_format;         /* G2048_BOARDS_BYTES (0) or G2048_BOARDS_NIBBLE: what g2048_env_step_host   */
+                                 /* writes to out->boards                                                      */
 } G2048EnvConfig;
+
+/* G2048EnvConfig.board_format.  The step is PCIe-bound for a host caller (21 bytes per board come back);  */
+/* nibble boards cut that to 13: out->boards is then [n*8], 4 bits per cell (see G2048StepArgs.boards_     */
+/* nibble).  A board holding a tile >= 65536 does not fit: such boards are counted in                     */
+/* out->nibble_overflow and g2048_env_get_boards_host returns the full 16-byte boards.                    */
+#define G2048_BOARDS_BYTES  0u
+#define G2048_BOARDS_NIBBLE 1u
 
 /* Host result pointers for g2048_env_step_host; boards/rewards/dones required. */
 typedef struct G2048HostStepOut {
-  uint8_t*  boards;       /* [n*16] */
+  uint8_t*  boards;       /* [n*16], or [n*8] with G2048_BOARDS_NIBBLE */
   float*    rewards;      /* [n]    */
   uint8_t*  dones;        /* [n]    */
   uint8_t*  illegal;      /* [n] nullable */
   uint8_t*  highest_exp;  /* [n] nullable */
   uint8_t*  legal_mask;   /* [n] nullable */
+  uint32_t* nibble_overflow; /* host uint32, nullable: boards of this step that do not fit G2048_BOARDS_NIBBLE */
 } G2048HostStepOut;
 
 int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg);
@@ -426,6 +451,8 @@ int g2048_env_step_host(G2048Env* env, const uint8_t* actions_host,
 int g2048_env_device_ptrs(G2048Env* env, uint8_t** boards, float** rewards,
                           uint8_t** dones);
 int g2048_env_set_boards_host(G2048Env* env, const uint8_t* boards_host);
+/* the live boards in the 16-byte format, whatever board_format is (synchronous) */
+int g2048_env_get_boards_host(G2048Env* env, uint8_t* boards_host);
 uint64_t g2048_env_step_index(const G2048Env* env);
 
 #ifdef __cplusplus

@@ -24,12 +24,14 @@ class StepArgs(C.Structure):
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
         ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
+        ("boards_nibble", C.c_void_p), ("nibble_overflow", C.c_void_p),
     ]
 
 
 def build(force=False):
     src = os.path.join(_HERE, "g2048_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "g2048.h")      # the argument structs come from the public header
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _SO
 

@@ -32,7 +32,7 @@ def build(specs):
             print(r.stderr)
             raise SystemExit(1)
         lines = r.stderr.splitlines()
-        info = [lines[i + 2].strip() for i, l in enumerate(lines) if "step_kernelILj0ELb0E" in l and "Compiling" in l]
+        info = [lines[i + 2].strip() for i, l in enumerate(lines) if "step_kernelILj0ELb0ELi0E" in l and "Compiling" in l]
         print(name, flags, info)
 
 

@@ -12,7 +12,7 @@ FMA = {"IMAD", "FADD", "FMUL", "FFMA", "HFMA2"}
 
 def main():
     so = sys.argv[1] if len(sys.argv) > 1 else "gym-2048_b200/libg2048.so"
-    pat = sys.argv[2] if len(sys.argv) > 2 else "step_kernelILj0ELb0E"
+    pat = sys.argv[2] if len(sys.argv) > 2 else "step_kernelILj0ELb0ELi0E"
     txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
     name, body = None, []
     for l in txt.splitlines():

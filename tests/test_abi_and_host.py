@@ -45,6 +45,8 @@ def test_struct_layouts_match_header():
       printf("%zu %zu %zu %zu %zu\n", offsetof(G2048StepArgs, boards_out), offsetof(G2048StepArgs, ep_return),
              offsetof(G2048StepArgs, final_return), sizeof(G2048OneIO), offsetof(G2048OneIO, reward));
       printf("%zu %zu\n", offsetof(G2048OneIO, done), offsetof(G2048OneIO, bad_cells));
+      printf("%zu %zu %zu\n", offsetof(G2048StepArgs, boards_nibble), offsetof(G2048StepArgs, nibble_overflow),
+             offsetof(G2048EnvConfig, board_format));
       return 0;
     }'''
     d = os.path.join(ROOT, "tests", "host_sim")
@@ -62,6 +64,9 @@ def test_struct_layouts_match_header():
     for S in (g._lib.StepArgs, oracle.StepArgs):
         assert [S.boards_out.offset, S.ep_return.offset, S.final_return.offset] == out[10:13]
     assert [C.sizeof(O), O.reward.offset, O.done.offset, O.bad_cells.offset] == [out[13], out[14], out[15], out[16]]
+    for S in (g._lib.StepArgs, oracle.StepArgs):
+        assert [S.boards_nibble.offset, S.nibble_overflow.offset] == out[17:19]
+    assert g._lib.EnvConfig.board_format.offset == out[19]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
@@ -119,8 +124,20 @@ def test_argument_checks_that_need_no_gpu():
     fake = 0x10000                      # never dereferenced: every call below fails validation first
     a = g._lib.StepArgs()
     a.boards, a.actions, a.rewards, a.dones, a.n = fake, fake, fake, fake, 8
-    a.flags = g._lib.FLAG_AUTO_RESET | g._lib.FLAG_POLICY_LEGAL
+    a.flags = g._lib.FLAG_AUTO_RESET | 64
     assert L.g2048_step(C.byref(a), None) == -1 and b"unknown flags" in L.g2048_last_error()
+    a.flags = g._lib.FLAG_AUTO_RESET | g._lib.FLAG_POLICY_LEGAL            # the random-legal policy reads legal_mask
+    assert L.g2048_step(C.byref(a), None) == -1 and b"legal_mask" in L.g2048_last_error()
+    a.flags = g._lib.FLAG_POLICY_UNIFORM | g._lib.FLAG_POLICY_LEGAL
+    assert L.g2048_step(C.byref(a), None) == -1 and b"choose one" in L.g2048_last_error()
+    a.flags = g._lib.FLAG_AUTO_RESET
+    assert L.g2048_step_n(C.byref(a), 4, 3, None) == -1 and b"row_stride" in L.g2048_last_error()
+    a.step_counter = fake
+    assert L.g2048_step_n(C.byref(a), 4, 8, None) == -1 and b"step_counter" in L.g2048_last_error()
+    a.step_counter = None
+    assert L.g2048_step_list(None, 3, None) == -1 and L.g2048_step_list(None, 0, None) == 0
+    assert L.g2048_one(None, 0, 0, 0, 0, 0, 0.0, 0, None, 1) == -1 and b"io is NULL" in L.g2048_last_error()
+    assert L.g2048_one(fake, 9, 0, 0, 0, 0, 0.0, 0, None, 1) == -1 and b"unknown op" in L.g2048_last_error()
     a.flags, a.max_tile_exp = g._lib.FLAG_AUTO_RESET, 64
     assert L.g2048_step(C.byref(a), None) == -1 and b"max_tile_exp" in L.g2048_last_error()
     a.max_tile_exp, a.boards = 0, fake + 4

@@ -261,6 +261,41 @@ def test_host_stepped_env_matches_oracle(g, extras):
     h.close()
 
 
+def test_host_stepped_env_nibble_boards(g):
+    """board_format='nibble': the same step, the boards coming back 4 bits per cell (13 instead of 21 bytes per board
+    over PCIe); boards that do not fit are counted and the full boards stay available."""
+    import torch
+    n = 30000
+    h = g.HostSteppedEnv(n, seed=9, n_chunks=3, board_format="nibble")
+    o = oracle.OracleBatch(n, seed=9, threads=4)
+    assert np.array_equal(h.reset().numpy(), o.reset())
+    rng = np.random.default_rng(1)
+    for t in range(25):
+        act = rng.integers(0, 4, n).astype(np.uint8)
+        b = h.step(act)
+        out = o.step(act)
+        assert b.boards.shape == (n, 8)
+        assert np.array_equal(b.unpacked_boards().numpy(), o.boards)
+        assert np.array_equal(b.rewards.numpy(), out["rewards"]) and np.array_equal(b.dones.numpy(), out["dones"])
+        assert b.nibble_overflow.value == 0
+    assert np.array_equal(h.full_boards().numpy(), o.boards)
+    # boards with tiles >= 65,536 do not fit 4 bits: counted, and the 16-byte boards are still there
+    big = o.boards.copy()
+    big[:7, 0] = 16
+    big[:7, 1] = 17
+    big[:7, 2:] = 0
+    check = g._lib.check
+    check(h.lib.g2048_env_set_boards_host(h._h, big.ctypes.data))
+    o.boards[:] = big
+    act = np.full(n, 2, np.uint8)                      # Down: the two big tiles stay on the board
+    b = h.step(act)
+    o.step(act)
+    assert b.nibble_overflow.value == 7
+    assert np.array_equal(h.full_boards().numpy(), o.boards)
+    assert np.array_equal(b.unpacked_boards().numpy()[7:], o.boards[7:])
+    h.close()
+
+
 def test_checkpoint_resume_is_exact(g):
     import torch
     n = 4096

@@ -475,3 +475,36 @@ def test_step_schedule_equals_eager_round_robin():
     for a, b in zip(A, B):
         assert torch.equal(a.boards, b.boards) and torch.equal(a.rewards, b.rewards) and torch.equal(a._dones, b._dones)
     assert torch.equal(A[1].legal_mask, B[1].legal_mask)
+
+
+@pytest.mark.parametrize("policy,n,T,kw", [
+    ("uniform", 5000, 30, {}),
+    ("legal", 70001, 120, dict(illegal_move_reward=-1.0)),
+    ("legal", 1 << 18, 40, dict(env_id_base=2**32 - 1000)),      # BASELINE config 4's size; ids cross 2^32
+])
+def test_step_with_in_kernel_policy_is_sample_actions_plus_step(policy, n, T, kw):
+    """step(policy=...) — action drawn and played in ONE launch — == sample_actions() followed by step(), and the
+    oracle's rollout under those actions; the legal policy never plays an illegal move while one is legal."""
+    import torch
+    import gym_2048_b200 as g
+    outs = ("legal_mask", "illegal") if policy == "legal" else ()
+    mk = lambda: g.BatchedGame2048(n, seed=31, outputs=outs, **kw)         # noqa: E731
+    a, b = mk(), mk()
+    a.reset(), b.reset()
+    ref = oracle.OracleBatch(n, seed=31, threads=4, env_id_base=kw.get("env_id_base", 0),
+                             illegal_move_reward=kw.get("illegal_move_reward", 0.0))
+    ref.reset()
+    n_illegal = 0
+    for t in range(T):
+        ra = a.step(policy=policy)
+        act = b.sample_actions(legal=(policy == "legal"))
+        rb = b.step(act)
+        assert torch.equal(ra.actions, act), t
+        assert torch.equal(ra.boards, rb.boards) and torch.equal(ra.rewards, rb.rewards) and torch.equal(ra.dones, rb.dones)
+        o = ref.step(act.cpu().numpy())
+        assert np.array_equal(ra.boards.cpu().numpy(), ref.boards)
+        if policy == "legal":
+            assert torch.equal(ra.legal_mask, rb.legal_mask)
+            assert np.array_equal(ra.legal_mask.cpu().numpy(), o["legal_mask"])
+            n_illegal += int(ra.illegal.sum())
+    assert policy != "legal" or n_illegal == 0
