@@ -610,8 +610,10 @@ def main():
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra block at N > 1")
     ap.add_argument("--sets", type=int, default=32)
-    ap.add_argument("--small-below", type=int, default=148 * 1024,
-                    help="shards smaller than this are issued through g2048_step_list (K launches per C call)")
+    ap.add_argument("--small-below", type=int, default=1 << 20,
+                    help="shards smaller than this are issued through g2048_step_list (K launches per C call): a "
+                         "Python loop issues a launch every ~6 us, a B200 steps 524,288 boards in ~6.5 us and "
+                         "131,072 in ~3 us (profiles/r02_launch_rate.log)")
     ap.add_argument("--action-pool", type=int, default=16)
     ap.add_argument("--fused-steps", type=int, default=32, help="steps per g2048_step_many launch (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=200)

@@ -110,11 +110,23 @@ unsigned grid_for_streaming(uint64_t n) {
 // 128 CTAs of 512 threads land on 64 SMs, two each, and leave 84 idle), the residency limit itself is set to
 // the even share, ceil(CTAs / SMs), by padding every CTA with dynamic shared memory it never touches.
 struct LaunchShape { unsigned grid, block; size_t pad_smem; };
-static LaunchShape shape_for(uint64_t n, size_t static_smem) {
+#ifndef G2048_SMALL_BLOCK      // 0: choose the CTA width of a small batch from its size (below); else force it (experiments)
+#define G2048_SMALL_BLOCK 0
+#endif
+static LaunchShape shape_for(uint64_t n, size_t static_smem, bool single_step) {
   const uint64_t sms = (uint64_t)sm_count();
   const uint64_t full_ctas = (n + kStepThreads - 1) / kStepThreads;
   if (full_ctas >= sms * kStepCtasPerSm) return LaunchShape{(unsigned)(sms * kStepCtasPerSm), (unsigned)kStepThreads, 0};
-  const unsigned block = 128u;
+  // One board per thread.  The widest CTA that still gives every SM one: each CTA pays a prologue (a 16 KB table
+  // copy, a barrier) and narrow CTAs multiply it — 131,072 boards run in 2.77 us as 256 CTAs of 512 threads and in
+  // 3.47 us as 1024 CTAs of 128 (profiles/r02_variants.log) — while too few CTAs leave SMs idle (65,536 boards as
+  // 64 CTAs of 1024 use 64 of 148 SMs).
+  // (The multi-step kernel runs for many steps per launch: its prologue is amortised, it keeps 128-thread CTAs.)
+  unsigned block = G2048_SMALL_BLOCK;
+  if (block == 0) {
+    block = single_step ? 1024u : 128u;
+    while (block > 128u && (n + block - 1) / block < sms) block >>= 1;
+  }
   const uint64_t ctas = (n + block - 1) / block;
   const uint64_t per_sm = (ctas + sms - 1) / sms;                          // 1 .. 8
   const size_t budget = (size_t)220 * 1024 / per_sm;                       // of the 227 KB an SM can carve out
@@ -137,6 +149,10 @@ static bool first_use_on_current_device(uint64_t& seen) {
 // kernels
 // ------------------------------------------------------------------------------------
 constexpr uint32_t kFlagBumpCounter = 0x80000000u;   // internal: this launch advances *step_counter when it ends
+constexpr uint32_t kFlagPrefetch = 0x40000000u;      // internal: L2-prefetch the first boards before griddepcontrol.wait
+#ifndef G2048_PREFETCH_MIN_N   // the prologue prefetch pays from this batch size on (3.47 -> 3.16 us WITHOUT it at 131,072
+#define G2048_PREFETCH_MIN_N 200000   // boards, 4.74 -> 4.24 us with it at 262,144, 11.5 -> 11.0 us at 1 Mi; profiles/r02_variants.log)
+#endif
 
 struct StepParams {
   const uint4* boards;
@@ -411,7 +427,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
   // with nothing to compute meanwhile.  An L2 prefetch has no architectural effect (the L2 is the point of
   // coherence: a line the previous launch is still writing is simply already there), so the first lines can be
   // requested while the previous launch drains: one lane per 128-byte line (8 boards), one per warp for the actions.
-  if (i < n) {
+  if (i < n && (p.flags & kFlagPrefetch)) {
     if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.boards + i));
     if (POLICY != 1 && (threadIdx.x & 31u) == 0u)
       asm volatile("prefetch.global.L2 [%0];" ::"l"((POLICY == 2 ? p.legal_mask : p.actions) + i));
@@ -1144,7 +1160,8 @@ static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepPara
   p.actions_out = const_cast<uint8_t*>(a->actions);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
-  p.flags = (a->flags & ~kFlagBumpCounter) | (bump_counter ? kFlagBumpCounter : 0u);
+  p.flags = (a->flags & ~(kFlagBumpCounter | kFlagPrefetch)) | (bump_counter ? kFlagBumpCounter : 0u) |
+            (a->n >= G2048_PREFETCH_MIN_N ? kFlagPrefetch : 0u);
 }
 
 // Launch configuration of a step over n boards (shape_for), with the kernel attributes it relies on set once per
@@ -1158,7 +1175,7 @@ static void step_launch_config(uint64_t n, cudaStream_t s, cudaLaunchConfig_t& c
   }
   cfg.blockDim = dim3(kStepThreads);
 #elif G2048_PERSISTENT
-  const LaunchShape shape = shape_for(n, sizeof(PairLut) + 256);
+  const LaunchShape shape = shape_for(n, sizeof(PairLut) + 256, true);
   cfg.gridDim = dim3(shape.grid);
   cfg.blockDim = dim3(shape.block);
   cfg.dynamicSmemBytes = shape.pad_smem;
@@ -1333,7 +1350,7 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
   p.flags = a->flags;
-  const LaunchShape shape = shape_for(m, sizeof(PairLut) + 256);
+  const LaunchShape shape = shape_for(m, sizeof(PairLut) + 256, false);
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(shape.grid);

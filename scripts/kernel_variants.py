@@ -37,6 +37,7 @@ def build(specs):
 
 
 def run(n=1 << 20, steps=3000, sets=8):
+    sets = int(os.environ.get("G2048_VARIANT_SETS", sets))
     import torch
     from gym_2048_b200._lib import StepArgs
     dev = torch.device("cuda", 0)
@@ -78,11 +79,26 @@ def run(n=1 << 20, steps=3000, sets=8):
             ref_boards = snap
         ok = bool(torch.equal(snap, ref_boards))
         best = None
+        # small batches: a Python loop cannot issue launches fast enough — pre-build the calls, one C call issues them
+        use_list = n < (1 << 19) and hasattr(L, "g2048_step_list")
+        if use_list:
+            L.g2048_step_list.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         for rep in range(3):
+            if use_list:
+                arr = (StepArgs * steps)()
+                for j, t in enumerate(range(64 + rep * steps, 64 + (rep + 1) * steps)):
+                    C.memmove(C.byref(arr[j]), C.byref(args), C.sizeof(StepArgs))
+                    arr[j].boards = boards[t % sets].data_ptr()
+                    arr[j].actions = acts[t % 16].data_ptr()
+                    arr[j].env_id_base = (t % sets) * n
+                    arr[j].step_index = t
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for t in range(64, 64 + steps):
-                step(t)
+            if use_list:
+                assert L.g2048_step_list(C.byref(arr), steps, stream) == 0, L.g2048_last_error()
+            else:
+                for t in range(64 + rep * steps, 64 + (rep + 1) * steps):
+                    step(t)
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / steps
