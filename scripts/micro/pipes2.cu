@@ -7,8 +7,8 @@
 #include <cuda_runtime.h>
 
 #define CHAINS 4
-enum Kind { LOP3, IMAD, VABS, VSAD, POPC, SHFV, IADD3, FADD, FFMA, HADD2, I2FP, DP4A, PRMTV, SELP, IMADHI, FLOP, BREV, LEAV, FMNMX, IMNMX, KINDS };
-static const char* kNames[] = {"LOP3", "IMAD", "VABSDIFF4", "VABSDIFF4.ACC", "POPC", "SHF", "IADD3", "FADD", "FFMA", "HADD2", "I2FP", "IDP.4A", "PRMT", "ISETP+SEL", "IMAD.HI", "FLO", "BREV", "LEA", "FMNMX", "VIMNMX"};
+enum Kind { LOP3, IMAD, VABS, VSAD, POPC, SHFV, IADD3, FADD, FFMA, HADD2, I2FP, DP4A, PRMTV, SELP, IMADHI, FLOP, BREV, LEAV, FMNMX, IMNMX, PRMTR, LOP3I, IMADW, SHFC, ISETPV, VIADDV, KINDS };
+static const char* kNames[] = {"LOP3", "IMAD", "VABSDIFF4", "VABSDIFF4.ACC", "POPC", "SHF", "IADD3", "FADD", "FFMA", "HADD2", "I2FP", "IDP.4A", "PRMT", "ISETP+SEL", "IMAD.HI", "FLO", "BREV", "LEA", "FMNMX", "VIMNMX", "PRMT (reg selector)", "LOP3 (imm operand)", "IMAD.WIDE", "SHF (const)", "ISETP only", "VIADD (imm)"};
 
 template <int K> __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, uint32_t one) {
   if (K == LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(one));
@@ -31,6 +31,12 @@ template <int K> __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, ui
   else if (K == LEAV) asm volatile("{ .reg .u32 t; shl.b32 t, %0, 3; add.u32 %0, t, %1; }" : "+r"(a) : "r"(b));
   else if (K == FMNMX) asm volatile("min.f32 %0, %0, %1;" : "+f"(*(float*)&a) : "f"(*(float*)&b));
   else if (K == IMNMX) asm volatile("min.u32 %0, %0, %1;" : "+r"(a) : "r"(b));
+  else if (K == PRMTR) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(one));
+  else if (K == LOP3I) asm volatile("lop3.b32 %0, %0, %1, 0x7f7f7f7f, 0x96;" : "+r"(a) : "r"(b));
+  else if (K == IMADW) { unsigned long long w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(a), "r"(0xD256D193u)); a = (uint32_t)(w >> 32) ^ (uint32_t)w; }
+  else if (K == SHFC) asm volatile("shr.u32 %0, %0, 7;" : "+r"(a));
+  else if (K == ISETPV) asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; @p add.u32 %0, %0, 1; }" : "+r"(a) : "r"(b));
+  else if (K == VIADDV) asm volatile("add.u32 %0, %0, 0x7f7f7f7f;" : "+r"(a));
 }
 
 template <int K1, int K2>
@@ -72,15 +78,40 @@ template <int K1, int K2> double run(int ctas_per_sm) {
   return warp_instr / cycles / (sms * 4);
 }
 
+// dependent-issue latency: ONE warp per SM sub-partition, ONE dependent chain
+template <int K>
+__global__ void __launch_bounds__(128) klat(uint32_t* out, uint32_t one, uint32_t seed, int iters) {
+  uint32_t a = seed + threadIdx.x * 7, b = seed ^ 0x9E3779B9u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) op<K>(a, b, one);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a + b;
+}
+template <int K> double latency() {
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int iters = 4000;
+  uint32_t* out; cudaMalloc(&out, sms * 128 * 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  klat<K><<<sms, 128>>>(out, 1, 3, 10);
+  cudaEventRecord(e0);
+  klat<K><<<sms, 128>>>(out, 1, 3, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  cudaFree(out);
+  return ms * 1e-3 * clk * 1e3 / ((double)iters * 32);
+}
+
 template <int K> void row() {
-  printf("%-14s alone %.3f   with LOP3 %.3f   with IMAD %.3f   with FADD %.3f\n", kNames[K], run<K, -1>(4), run<K, LOP3>(4),
-         run<K, IMAD>(4), run<K, FADD>(4));
+  printf("%-20s alone %.3f   with LOP3 %.3f   with IMAD %.3f   with FADD %.3f   dependent-issue latency %.1f cycles\n", kNames[K],
+         run<K, -1>(4), run<K, LOP3>(4), run<K, IMAD>(4), run<K, FADD>(4), latency<K>());
 }
 
 int main() {
   printf("PTX ops per cycle per SM sub-partition, 8 warps/SMSP, 4 independent chains per thread\n");
   row<LOP3>(); row<IMAD>(); row<IMADHI>(); row<PRMTV>(); row<SHFV>(); row<IADD3>(); row<VABS>(); row<VSAD>(); row<POPC>();
   row<FLOP>(); row<BREV>(); row<SELP>(); row<LEAV>(); row<IMNMX>(); row<FADD>(); row<FFMA>(); row<FMNMX>(); row<HADD2>();
-  row<I2FP>(); row<DP4A>();
+  row<I2FP>(); row<DP4A>(); row<PRMTR>(); row<LOP3I>(); row<IMADW>(); row<SHFC>(); row<ISETPV>(); row<VIADDV>();
   return 0;
 }
