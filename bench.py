@@ -318,7 +318,7 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
         for j in range(total):
             sched.add(games[j % S], pool[j % P])
         sched.build()
-        issue = "g2048_step_list via StepSchedule (K launches per C call; one kernel launch per env step)"
+        issue = "g2048_step_list_timed via StepSchedule (all regions in one C call; one kernel launch per env step)"
 
         def run(lo, hi):
             sched.run(lo, hi)
@@ -329,6 +329,8 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
             for j in range(lo, hi):
                 games[j % S].step(pool[j % P])
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    for e in ev:
+        e.record()                                 # creates the cudaEvent_t handles (torch does it lazily)
     torch.cuda.synchronize()
     barrier()
     # no host sleep, synchronisation or barrier between the spin-up, the warm-up and the timed regions: the
@@ -336,12 +338,17 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
     run(0, spinup)
     run(spinup, spinup + W)
     t_start = time.perf_counter()
-    ev[0].record()
     at = spinup + W
-    for r in range(R):
-        run(at, at + K)
-        at += K
-        ev[r + 1].record()
+    if small:
+        # all R regions from ONE C call, the events recorded between them by the library: ~10 us of interpreter per
+        # region would otherwise be a fifth of a region of twenty 3-us launches
+        sched.run(at, at + R * K, events=ev, every=K)
+    else:
+        ev[0].record()
+        for r in range(R):
+            run(at, at + K)
+            at += K
+            ev[r + 1].record()
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     barrier()
@@ -487,12 +494,11 @@ def run_ours(args):
             sched.add(g4[j % S4], acts4[j % S4], policy="legal")
         sched.build()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(R4 + 1)]
+        for e in ev:
+            e.record()
         torch.cuda.synchronize()
         sched.run(0, spin4)
-        ev[0].record()
-        for r in range(R4):
-            sched.run(spin4 + r * K4, spin4 + (r + 1) * K4)
-            ev[r + 1].record()
+        sched.run(spin4, spin4 + R4 * K4, events=ev, every=K4)
         torch.cuda.synchronize()
         m4 = statistics.median(ev[r].elapsed_time(ev[r + 1]) for r in range(R4)) / K4          # ms per step
         empties = float((g4[0].boards == 0).sum(dim=1).float().mean())
@@ -503,7 +509,7 @@ def run_ours(args):
                    "value": n4 / (m4 * 1e-3), "unit": UNIT, "us_per_step": m4 * 1e3, "launches_per_step": 1,
                    "kernel": "g2048_step_kernel<O_MASK, false, POLICY_LEGAL>", "algorithmic_bytes_per_step": bytes4,
                    "roofline_frac": bytes4 * n4 / (m4 * 1e-3) / 1e9 / peak4, "mean_empty_cells": empties,
-                   "issue": "g2048_step_list via StepSchedule", "steps": K4, "repeats": R4}
+                   "issue": "g2048_step_list_timed via StepSchedule", "steps": K4, "repeats": R4}
         del g4, acts4, sched
         torch.cuda.empty_cache()
 

@@ -23,7 +23,7 @@ FLAG_POLICY_UNIFORM, FLAG_POLICY_LEGAL = 2, 4
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
-    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_n", "g2048_step_list", "g2048_one", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
+    "g2048_abi_version", "g2048_last_error", "g2048_step", "g2048_step_n", "g2048_step_list", "g2048_step_list_timed", "g2048_one", "g2048_step_many", "g2048_reset", "g2048_add_tile", "g2048_move", "g2048_status",
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_get_boards_host", "g2048_env_step_index",
@@ -163,6 +163,7 @@ def lib():
     L.g2048_step.argtypes = [C.POINTER(StepArgs), vp]
     L.g2048_step_n.argtypes = [C.POINTER(StepArgs), u32, u64, vp]
     L.g2048_step_list.argtypes = [vp, u64, vp]
+    L.g2048_step_list_timed.argtypes = [vp, u64, u64, vp, u64, vp]
     L.g2048_one.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64, u64, C.c_float, u32, vp, C.c_int]
     L.g2048_step_many.argtypes = [C.POINTER(StepManyArgs), vp]
     L.g2048_reset.argtypes = [vp, vp, u64, u64, u64, u64, vp]

@@ -721,8 +721,11 @@ class StepSchedule:
             self._array, self._lib = arr, _lib.lib()
         return self._array
 
-    def run(self, lo=None, hi=None):
-        """Launch items [lo, hi) (default: everything not yet launched) on the current stream."""
+    def run(self, lo=None, hi=None, events=None, every=0):
+        """Launch items [lo, hi) (default: everything not yet launched) on the current stream.
+        events (a list of torch.cuda.Event(enable_timing=True)) with every = K: events[0] is recorded before the
+        first launch and events[r] after launch r*K, all from C (g2048_step_list_timed) — R timed regions of K
+        launches cost one trip through the interpreter instead of R."""
         arr = self.build()
         lo = self._next if lo is None else int(lo)
         hi = len(self._items) if hi is None else int(hi)
@@ -732,11 +735,20 @@ class StepSchedule:
             return
         idx = self._device.index
         ptr = C.c_void_p(C.addressof(arr) + lo * C.sizeof(StepArgs))
+
+        def call():
+            if not events:
+                return self._lib.g2048_step_list(ptr, hi - lo, _raw_stream(idx))
+            for e in events:                       # torch creates the cudaEvent_t lazily, at the first record()
+                if not e.cuda_event:
+                    e.record()
+            handles = (C.c_void_p * len(events))(*[e.cuda_event for e in events])
+            return self._lib.g2048_step_list_timed(ptr, hi - lo, int(every), handles, len(events), _raw_stream(idx))
         if torch.cuda.current_device() == idx:
-            rc = self._lib.g2048_step_list(ptr, hi - lo, _raw_stream(idx))
+            rc = call()
         else:
             with torch.cuda.device(idx):
-                rc = self._lib.g2048_step_list(ptr, hi - lo, _raw_stream(idx))
+                rc = call()
         self._next = hi
         if rc:
             check(rc)

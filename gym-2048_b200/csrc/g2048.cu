@@ -79,10 +79,26 @@ constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 constexpr int kStepThreads = G2048_STEP_THREADS, kStepCtasPerSm = G2048_STEP_CTAS_PER_SM;
 static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");
 
+// The current device of the calling thread.  A launch list (g2048_step_list) issues thousands of launches on one
+// device: it pins the answer for its duration instead of asking the runtime twice per launch.
+static thread_local int tl_device_hint = -1;
+static cudaError_t current_device(int* dev) {
+  if (tl_device_hint >= 0) { *dev = tl_device_hint; return cudaSuccess; }
+  return cudaGetDevice(dev);
+}
+struct DeviceHint {
+  bool set;
+  DeviceHint() : set(false) {
+    int dev = -1;
+    if (tl_device_hint < 0 && cudaGetDevice(&dev) == cudaSuccess) { tl_device_hint = dev; set = true; }
+  }
+  ~DeviceHint() { if (set) tl_device_hint = -1; }
+};
+
 static int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (current_device(&dev) != cudaSuccess) return 148;
   if (dev != cached_dev) {
     if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
     cached_dev = dev;
@@ -138,7 +154,7 @@ constexpr int kMaxPadSmem = 208 * 1024;
 // kernel attributes are per device and are set once, also for a host thread that drives several GPUs in turn.
 static bool first_use_on_current_device(uint64_t& seen) {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  if (current_device(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
   const uint64_t bit = 1ull << dev;
   if (seen & bit) return false;
   seen |= bit;
@@ -1277,6 +1293,7 @@ int g2048_step_n(const G2048StepArgs* a, uint32_t n_steps, uint64_t row_stride, 
   if (!aligned16(a->terminal_boards ? a->terminal_boards + 16 * row_stride : nullptr))
     return fail(G2048_ERR_ALIGN, "g2048_step_n: terminal_boards rows must stay 16-byte aligned");
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const DeviceHint pin_device;
   G2048StepArgs k = *a;
   for (uint32_t t = 0; t < n_steps; ++t) {
     const int rc = issue_step(&k, s);
@@ -1298,24 +1315,43 @@ int g2048_step_n(const G2048StepArgs* a, uint32_t n_steps, uint64_t row_stride, 
 }
 
 // A caller-built list of steps, issued by one call: element j is a complete g2048_step call (its own boards, rows,
-// step index ...), launched in order on `stream`.  The elements may belong to different env sets.
-int g2048_step_list(const G2048StepArgs* list, uint64_t count, void* stream) {
+// step index ...), launched in order on `stream`.  The elements may belong to different env sets.  With `events`
+// (cudaEvent_t handles): events[0] is recorded before the first launch and events[r] after launch r * every — a whole
+// timed run (R regions of `every` launches) is then ONE trip through the caller's interpreter.
+static int step_list(const G2048StepArgs* list, uint64_t count, uint64_t every, void* const* events, uint64_t n_events,
+                     void* stream, const char* fn) {
   if (count == 0) return G2048_OK;
-  if (!list) return fail(G2048_ERR_INVALID, "g2048_step_list: list is NULL");
+  if (!list) return fail(G2048_ERR_INVALID, "%s: list is NULL", fn);
+  if (n_events && (!events || every == 0)) return fail(G2048_ERR_INVALID, "%s: events need an array and every > 0", fn);
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const DeviceHint pin_device;
+  uint64_t next_event = 0;
+  if (n_events) G2048_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[next_event++]), s));
   for (uint64_t j = 0; j < count; ++j) {
     const G2048StepArgs* a = list + j;
-    const int bad = check_step_args(a, "g2048_step_list");
+    const int bad = check_step_args(a, fn);
     if (bad) {
       char first[sizeof g_err];
       std::snprintf(first, sizeof first, "%s", g_err);
-      return fail(bad, "g2048_step_list: element %llu: %s", (unsigned long long)j, first);
+      return fail(bad, "%s: element %llu: %s", fn, (unsigned long long)j, first);
     }
-    if (a->n == 0) continue;
-    const int rc = issue_step(a, s);
-    if (rc != G2048_OK) return rc;
+    if (a->n != 0) {
+      const int rc = issue_step(a, s);
+      if (rc != G2048_OK) return rc;
+    }
+    if (next_event < n_events && (j + 1) % every == 0)
+      G2048_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[next_event++]), s));
   }
   return launch_check("g2048_step_kernel");
+}
+
+int g2048_step_list(const G2048StepArgs* list, uint64_t count, void* stream) {
+  return step_list(list, count, 0, nullptr, 0, stream, "g2048_step_list");
+}
+
+int g2048_step_list_timed(const G2048StepArgs* list, uint64_t count, uint64_t every, void* const* events,
+                          uint64_t n_events, void* stream) {
+  return step_list(list, count, every, events, n_events, stream, "g2048_step_list_timed");
 }
 
 // lean, with optional outputs, uniform policy, random-legal policy

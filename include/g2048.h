@@ -174,6 +174,14 @@ int g2048_step_n(const G2048StepArgs* args, uint32_t n_steps, uint64_t row_strid
  * step_index + 1).  Fails on the first invalid element; earlier elements stay launched.
  */
 int g2048_step_list(const G2048StepArgs* list, uint64_t count, void* stream);
+/*
+ * The same, with CUDA events (cudaEvent_t handles as void*) recorded on the stream: events[0]
+ * before the first launch, events[r] after launch r*every (r = 1 .. n_events-1, as far as the
+ * list goes).  A benchmark's R timed regions of `every` launches are one C call: on shards a
+ * GPU steps in ~3 us the interpreter's ~10 us per region would otherwise be what is measured.
+ */
+int g2048_step_list_timed(const G2048StepArgs* list, uint64_t count, uint64_t every,
+                          void* const* events, uint64_t n_events, void* stream);
 
 /*
  * n_steps steps in one launch, for open-loop action sequences (pre-generated random

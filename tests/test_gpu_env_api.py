@@ -331,3 +331,38 @@ def test_argument_validation(g):
     buf = torch.zeros(4 * 16 + 1, dtype=torch.uint8, device="cuda")
     assert L.g2048_reset(C.c_void_p(buf.data_ptr() + 1), None, 4, 0, 0, 0, None) == -2
     assert L.g2048_encode_obs(C.c_void_p(buf.data_ptr()), C.c_void_p(buf.data_ptr()), 99, 1, None) == -1
+
+
+def test_bench_prints_one_contract_line_on_a_small_workload():
+    """bench.py on a small batch (fast): ONE JSON line with the contract's keys, the step-list issue path for a
+    shard the host cannot keep up with, and a state checksum that does not depend on how the run is timed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(*extra):
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--envs", "65536", "--steps", "4", "--warmup", "3",
+                            "--repeats", "3", "--spinup", "64", "--sets", "4", "--e2e-steps", "3", "--fused-steps", "4",
+                            "--no-cpu-baseline", "--no-config4"] + list(extra), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1, r.stdout
+        return json.loads(lines[0])
+    d = run()
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "repeats", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "e2e_compact", "gpu_launches", "clocks",
+              "state_checksum", "timing"):
+        assert k in d, k
+    assert d["metric"] == "env_steps_per_sec" and d["scaling"] == "strong" and d["dtype"] == "u8" and d["value"] > 1e9
+    assert d["config"]["global_envs"] == 65536 and d["gpu_launches"] == 12 and d["repeats"] == 3
+    assert "g2048_step_list" in d["timing"]["issue"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic_kind"]
+    assert abs(r["achieved"] - 38 * 65536 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert d["e2e"]["d2h_bytes_per_step"] == 65536 * 21 and d["e2e_compact"]["d2h_bytes_per_step"] == 65536 * 13
+    assert d["e2e"]["checksum"] == d["e2e_compact"]["checksum"]          # same rewards through both host formats
+    # the Python-loop issue path (forced) steps the same boards: identical checksum
+    d2 = run("--small-below", "0")
+    assert "Python loop" in d2["timing"]["issue"] and d2["state_checksum"] == d["state_checksum"]

@@ -508,3 +508,24 @@ def test_step_with_in_kernel_policy_is_sample_actions_plus_step(policy, n, T, kw
             assert np.array_equal(ra.legal_mask.cpu().numpy(), o["legal_mask"])
             n_illegal += int(ra.illegal.sum())
     assert policy != "legal" or n_illegal == 0
+
+
+def test_step_schedule_timed_run_records_events_between_regions():
+    """StepSchedule.run(events=..., every=K): same boards as the untimed run, R + 1 events recorded in order."""
+    import torch
+    import gym_2048_b200 as g
+    n, K, R = 20000, 5, 4
+    a, b = (g.BatchedGame2048(n, seed=8, outputs=()) for _ in range(2))
+    a.reset(), b.reset()
+    acts = torch.randint(0, 4, (K * R, n), device="cuda", dtype=torch.uint8, generator=torch.Generator(device="cuda").manual_seed(3))
+    sa, sb = g.StepSchedule(), g.StepSchedule()
+    for j in range(K * R):
+        sa.add(a, acts[j])
+        sb.add(b, acts[j])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+    sa.run(events=ev, every=K)
+    sb.run()
+    torch.cuda.synchronize()
+    assert torch.equal(a.boards, b.boards)
+    ms = [ev[r].elapsed_time(ev[r + 1]) for r in range(R)]
+    assert all(m > 0 for m in ms)
