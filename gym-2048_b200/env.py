@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import check
-from .batched import tile_to_exp
+from .batched import _raw_stream, tile_to_exp
 
 try:  # gymnasium is optional: the class works without it and registers itself when present
     import gymnasium as _gym
@@ -102,11 +102,12 @@ class _Device:
         args = (self.ptr, op, int(action) & 3, 1 if trial else 0, seed, index, float(illegal_move_reward),
                 int(max_tile_exp))
         if torch.cuda.current_device() == self.index:
-            rc = self.lib.g2048_one(*args, torch.cuda.current_stream(self.dev).cuda_stream, 1)
+            rc = self.lib.g2048_one(*args, _raw_stream(self.index), 1)
         else:
             with torch.cuda.device(self.index):
-                rc = self.lib.g2048_one(*args, torch.cuda.current_stream(self.dev).cuda_stream, 1)
-        check(rc)
+                rc = self.lib.g2048_one(*args, _raw_stream(self.index), 1)
+        if rc:
+            check(rc)
         if need_valid and self.io.bad_cells:
             raise ValueError("board holds a cell that is not 0 or a power of two: %s" % (np.asarray(matrix),))
         return self.io
