@@ -623,7 +623,7 @@ def main():
     ap.add_argument("--action-pool", type=int, default=16)
     ap.add_argument("--fused-steps", type=int, default=32, help="steps per g2048_step_many launch (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--e2e-chunks", type=int, default=3)
+    ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--ref-steps-per-proc", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 extra block (N = 1)")

@@ -10,7 +10,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libg2048.so")
+SO_PATH = os.environ.get("G2048_SO") or os.path.join(_PKG, "libg2048.so")     # G2048_SO: a variant build (experiments)
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("g2048.cu", "g2048_data.cu", "g2048_csv.cpp")]
 HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_PKG, "csrc", "g2048_internal.h"),
            os.path.join(_ROOT, "include", "g2048.h")]
@@ -100,6 +100,8 @@ BOARDS_BYTES, BOARDS_NIBBLE = 0, 1
 
 
 def _stale():
+    if os.environ.get("G2048_SO"):
+        return False                    # an explicitly chosen library is used as it is
     if not os.path.exists(SO_PATH):
         return True
     t = os.path.getmtime(SO_PATH)

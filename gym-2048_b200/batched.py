@@ -581,7 +581,7 @@ class HostSteppedEnv:
         cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
                              int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
                              int(n_chunks), _lib.BOARDS_NIBBLE if nibble else _lib.BOARDS_BYTES)
-        self._n_chunks = min(int(n_chunks) if n_chunks else 3, 64)
+        self._n_chunks = min(int(n_chunks) if n_chunks else 2, 64)
         self._h = C.c_void_p()
         check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
         self.buffers = HostBuffers(self.num_envs, extras, nibble)

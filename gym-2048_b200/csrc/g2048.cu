@@ -1064,6 +1064,8 @@ struct G2048Env {
   uint32_t* h_overflow;         // pinned mirror of d_overflow
   cudaStream_t streams[4];
   int n_streams;
+  cudaEvent_t slice_done[64];   // slice c's kernel has finished (the small result copies wait for it on another stream)
+  int n_events;
 };
 
 using namespace g2048;
@@ -1596,6 +1598,7 @@ int g2048_env_destroy(G2048Env* e) {
   if (!e) return G2048_OK;
   cudaSetDevice(e->cfg.device);
   for (int i = 0; i < e->n_streams; ++i) cudaStreamDestroy(e->streams[i]);
+  for (int i = 0; i < e->n_events; ++i) cudaEventDestroy(e->slice_done[i]);
   cudaFree(e->d_boards); cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_dones);
   cudaFree(e->d_illegal); cudaFree(e->d_highest); cudaFree(e->d_mask);
   cudaFree(e->d_ep_score); cudaFree(e->d_ep_len); cudaFree(e->d_nibble); cudaFree(e->d_overflow);
@@ -1614,7 +1617,7 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   if (!e) return fail(G2048_ERR_NOMEM, "g2048_env_create: out of host memory");
   std::memset(e, 0, sizeof *e);
   e->cfg = *cfg;
-  e->n_chunks = cfg->n_chunks ? cfg->n_chunks : 3u;
+  e->n_chunks = cfg->n_chunks ? cfg->n_chunks : 2u;
   if (e->n_chunks > 64u) e->n_chunks = 64u;
   const uint64_t n = cfg->n;
   cudaError_t err = cudaSuccess;
@@ -1632,6 +1635,10 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   for (int i = 0; i < 4 && err == cudaSuccess; ++i) {
     err = cudaStreamCreateWithFlags(&e->streams[i], cudaStreamNonBlocking);
     if (err == cudaSuccess) e->n_streams = i + 1;
+  }
+  for (int i = 0; i < 64 && err == cudaSuccess; ++i) {
+    err = cudaEventCreateWithFlags(&e->slice_done[i], cudaEventDisableTiming);
+    if (err == cudaSuccess) e->n_events = i + 1;
   }
   if (err != cudaSuccess) {
     const int rc = err == cudaErrorMemoryAllocation ? fail(G2048_ERR_NOMEM, "g2048_env_create: %s", cudaGetErrorString(err))
@@ -1684,7 +1691,8 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   // Chunk schedule: a short lead chunk (n / lead_div boards) so that the first D2H copy starts a few
   // microseconds into the call, then the rest in n_chunks - 1 equal slices whose H2D copies and kernels
   // hide behind the D2H stream of their predecessors.
-  // (profiles/r01_e2e_chunks.log: 1/16 lead + 2 slices 0.463 ms per 1 Mi boards, equal thirds 0.488 ms.)
+  // (profiles/r01_e2e_chunks.log: 1/16 lead + 2 slices 0.463 ms per 1 Mi boards, equal thirds 0.488 ms;
+  //  profiles/r02_e2e_sweep.log: 1/16 lead + 1 slice 0.451 ms, + 2 slices 0.464 ms: the default is 2 chunks.)
   constexpr uint64_t lead_div = 16;
   uint64_t lead = 0;
   if (e->n_chunks >= 2 && n >= 65536) lead = (n / lead_div + 255) / 256 * 256;
@@ -1692,7 +1700,13 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   uint64_t per = (n - lead + rest_chunks - 1) / rest_chunks;
   per = (per + 255) / 256 * 256;
   const bool nibble = e->cfg.board_format == G2048_BOARDS_NIBBLE;
-  // One slice: H2D(actions) -> step kernel -> D2H(results), all on stream s.
+#ifndef G2048_E2E_SPLIT_COPIES   // 1: the small result arrays of a slice are copied on a second stream (another copy engine).
+#define G2048_E2E_SPLIT_COPIES 0   //    Measured (profiles/r02_e2e_sweep.log): no difference — the call is bound by the board
+#endif                             //    bytes over PCIe, not by per-copy set-up — so the simpler schedule ships.
+  // One slice: H2D(actions) -> step kernel -> D2H(boards) on stream s; the small result arrays (rewards, dones, ...)
+  // follow the kernel on the auxiliary stream, so that their per-copy set-up cost runs beside the board copies
+  // instead of between them.
+  const cudaStream_t aux = (G2048_E2E_SPLIT_COPIES && e->n_streams == 4) ? e->streams[3] : nullptr;
   auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s, int c) -> int {
     if (nibble) G2048_CUDA(cudaMemsetAsync(e->d_overflow + c, 0, 4, s));
     G2048_CUDA(cudaMemcpyAsync(e->d_actions + lo, actions_host + lo, m, cudaMemcpyHostToDevice, s));
@@ -1717,24 +1731,30 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     a.flags = e->cfg.flags;
     const int rc = g2048_step(&a, s);
     if (rc) return rc;
+    cudaStream_t s2 = s;
+    if (aux && c < e->n_events) {
+      G2048_CUDA(cudaEventRecord(e->slice_done[c], s));
+      G2048_CUDA(cudaStreamWaitEvent(aux, e->slice_done[c], 0));
+      s2 = aux;
+    }
     if (nibble) {
       G2048_CUDA(cudaMemcpyAsync(o->boards + 8 * lo, e->d_nibble + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, s));
-      G2048_CUDA(cudaMemcpyAsync(e->h_overflow + c, e->d_overflow + c, 4, cudaMemcpyDeviceToHost, s));
+      G2048_CUDA(cudaMemcpyAsync(e->h_overflow + c, e->d_overflow + c, 4, cudaMemcpyDeviceToHost, s2));
     } else {
       G2048_CUDA(cudaMemcpyAsync(o->boards + 16 * lo, e->d_boards + 16 * lo, 16 * m, cudaMemcpyDeviceToHost, s));
     }
-    G2048_CUDA(cudaMemcpyAsync(o->rewards + lo, e->d_rewards + lo, 4 * m, cudaMemcpyDeviceToHost, s));
-    G2048_CUDA(cudaMemcpyAsync(o->dones + lo, e->d_dones + lo, m, cudaMemcpyDeviceToHost, s));
-    if (o->illegal) G2048_CUDA(cudaMemcpyAsync(o->illegal + lo, e->d_illegal + lo, m, cudaMemcpyDeviceToHost, s));
-    if (o->highest_exp) G2048_CUDA(cudaMemcpyAsync(o->highest_exp + lo, e->d_highest + lo, m, cudaMemcpyDeviceToHost, s));
-    if (o->legal_mask) G2048_CUDA(cudaMemcpyAsync(o->legal_mask + lo, e->d_mask + lo, m, cudaMemcpyDeviceToHost, s));
+    G2048_CUDA(cudaMemcpyAsync(o->rewards + lo, e->d_rewards + lo, 4 * m, cudaMemcpyDeviceToHost, s2));
+    G2048_CUDA(cudaMemcpyAsync(o->dones + lo, e->d_dones + lo, m, cudaMemcpyDeviceToHost, s2));
+    if (o->illegal) G2048_CUDA(cudaMemcpyAsync(o->illegal + lo, e->d_illegal + lo, m, cudaMemcpyDeviceToHost, s2));
+    if (o->highest_exp) G2048_CUDA(cudaMemcpyAsync(o->highest_exp + lo, e->d_highest + lo, m, cudaMemcpyDeviceToHost, s2));
+    if (o->legal_mask) G2048_CUDA(cudaMemcpyAsync(o->legal_mask + lo, e->d_mask + lo, m, cudaMemcpyDeviceToHost, s2));
     return G2048_OK;
   };
   int c = 0;
   for (uint64_t lo = 0; lo < n; ++c) {
     const uint64_t want = (c == 0 && lead) ? lead : per;
     const uint64_t m = (n - lo < want) ? n - lo : want;
-    const int rc = issue_slice(lo, m, e->streams[c % e->n_streams], c);
+    const int rc = issue_slice(lo, m, e->streams[c % (aux ? 3 : e->n_streams)], c);
     if (rc) {
       // Some slices of this step may already have run.  Drain the streams (no work of the failed call is left
       // in flight over the caller's host buffers) and say that the env is no longer at a step boundary: the

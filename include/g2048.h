@@ -425,7 +425,7 @@ typedef struct G2048EnvConfig {
   uint64_t seed;
   float    illegal_move_reward;
   uint32_t max_tile_exp;
-  uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default (3: a 1/16 lead slice + 2) */
+  uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default (2: a 1/16 lead slice + the rest) */
   uint32_t board_format;         /* G2048_BOARDS_BYTES (0) or G2048_BOARDS_NIBBLE: what g2048_env_step_host   */
                                  /* writes to out->boards                                                      */
 } G2048EnvConfig;
