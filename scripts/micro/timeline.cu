@@ -32,6 +32,12 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(const P p) {
   __syncthreads();
   const uint32_t n = p.n, stride = gridDim.x * THREADS;
   uint32_t i = blockIdx.x * THREADS + threadIdx.x;
+#ifndef NO_PRE_PREFETCH
+  if (i < n) {      // the product's prologue prefetch (g2048.cu): first boards into the L2 while the previous launch drains
+    if ((threadIdx.x & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.boards + i));
+    if ((threadIdx.x & 31u) == 0u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + i));
+  }
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (TRACE && (threadIdx.x & 31) == 0) t_wait = gtime();
   if (i >= n) return;
@@ -69,7 +75,7 @@ __global__ void init_boards(uint4* b, uint8_t* a, uint32_t n, uint32_t salt) {
 }
 
 int main() {
-  const uint32_t n = 1u << 20; const int sets = 8, T = 512, C = 2;
+  const uint32_t n = 1u << 20; const int sets = 8, T = 1024, C = 1;
   int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const unsigned grid = sms * C;
   std::vector<uint4*> boards(sets);
@@ -78,8 +84,8 @@ int main() {
   cudaMalloc(&actions, (size_t)n * 8); cudaMalloc(&dones, n); cudaMalloc(&rewards, (size_t)n * 4);
   for (int s = 0; s < sets; ++s) init_boards<<<n / 256, 256>>>(boards[s], actions + (size_t)s * n, n, s);
   const int L = 40;                                 // traced launches
-  unsigned long long* trace; cudaMalloc(&trace, (size_t)L * grid * 16 * 4 * 8);
-  cudaMemset(trace, 0, (size_t)L * grid * 16 * 4 * 8);
+  unsigned long long* trace; cudaMalloc(&trace, (size_t)L * grid * (T / 32) * 4 * 8);
+  cudaMemset(trace, 0, (size_t)L * grid * (T / 32) * 4 * 8);
   cudaDeviceSynchronize();
   P p; p.actions = actions; p.rewards = rewards; p.dones = dones; p.n = n;
   cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T);
@@ -88,8 +94,8 @@ int main() {
   auto launch = [&](int t, bool tr, int slot) {
     p.boards = boards[t % sets]; p.actions = actions + (size_t)(t % 8) * n;
     make_stream_keys(stream_key(42, t, 0, 0), t, p.keys);
-    p.trace = trace + (size_t)slot * grid * 16 * 4;
-    if (tr) cudaLaunchKernelEx(&cfg, k<512, 2, true>, p); else cudaLaunchKernelEx(&cfg, k<512, 2, false>, p);
+    p.trace = trace + (size_t)slot * grid * (T / 32) * 4;
+    if (tr) cudaLaunchKernelEx(&cfg, k<1024, 1, true>, p); else cudaLaunchKernelEx(&cfg, k<1024, 1, false>, p);
   };
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int t = 0; t < 200; ++t) launch(t, false, 0);
@@ -104,7 +110,7 @@ int main() {
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   cudaEventElapsedTime(&ms, e0, e1);
   printf("traced:   %.2f us/launch\n", ms * 1e3 / L);
-  const unsigned W = grid * 16;
+  const unsigned WPC = T / 32, W = grid * WPC;
   std::vector<unsigned long long> h((size_t)L * W * 4);
   cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost);
   // distribution of warp end times, by SM, by warp index in the CTA
@@ -117,31 +123,32 @@ int main() {
     for (unsigned w = 0; w < W; ++w) next_rel = std::min(next_rel, tn[4 * w + 1]);
     std::vector<double> sm_end(sms, 0), sm_first(sms, 0);
     std::vector<double> ends, firsts;
-    double by_warp[16] = {0}, by_warp_first[16] = {0};
+    double by_warp[32] = {0}, by_warp_first[32] = {0};
     for (unsigned w = 0; w < W; ++w) {
       const double e = (double)t[4 * w + 3] - (double)base, f = (double)t[4 * w + 2] - (double)base;
       ends.push_back(e); firsts.push_back(f);
       const unsigned sm = (unsigned)t[4 * w + 0];
       sm_end[sm] = std::max(sm_end[sm], e); sm_first[sm] = std::max(sm_first[sm], f);
-      by_warp[w % 16] += e / grid; by_warp_first[w % 16] += f / grid;
+      by_warp[w % WPC] += e / grid; by_warp_first[w % WPC] += f / grid;
     }
     std::sort(ends.begin(), ends.end()); std::sort(firsts.begin(), firsts.end());
-    printf("launch %d: next release at %.0f ns after this release\n", l, (double)next_rel - (double)base);
+    printf("launch %d: next release at %.0f ns after this release; this launch's last warp ended at %.0f ns\n", l,
+           (double)next_rel - (double)base, ends[W - 1]);
     printf("  warp first-board-done percentiles 0/10/50/90/100: %.0f %.0f %.0f %.0f %.0f\n", firsts[0], firsts[W / 10], firsts[W / 2], firsts[W * 9 / 10], firsts[W - 1]);
     printf("  warp loop-end percentiles        0/10/50/90/100: %.0f %.0f %.0f %.0f %.0f\n", ends[0], ends[W / 10], ends[W / 2], ends[W * 9 / 10], ends[W - 1]);
     std::vector<double> se = sm_end; std::sort(se.begin(), se.end());
     printf("  per-SM last warp end percentiles 0/10/50/90/100: %.0f %.0f %.0f %.0f %.0f\n", se[0], se[sms / 10], se[sms / 2], se[sms * 9 / 10], se[sms - 1]);
     printf("  mean end by warp index in CTA:");
-    for (int q = 0; q < 16; ++q) printf(" %.0f", by_warp[q]);
+    for (unsigned q = 0; q < WPC; ++q) printf(" %.0f", by_warp[q]);
     if (l == L - 2) {
       for (unsigned smq = 0; smq < 2; ++smq) {
         printf("\n  SM %u warps (cta.warp first end):", smq);
         for (unsigned w = 0; w < W; ++w) if ((unsigned)t[4 * w + 0] == smq)
-          printf(" %u.%u %.1f %.1f |", w / 16, w % 16, ((double)t[4 * w + 2] - (double)base) / 1000., ((double)t[4 * w + 3] - (double)base) / 1000.);
+          printf(" %u.%u %.1f %.1f |", w / WPC, w % WPC, ((double)t[4 * w + 2] - (double)base) / 1000., ((double)t[4 * w + 3] - (double)base) / 1000.);
       }
     }
     printf("\n  mean first-done by warp index:");
-    for (int q = 0; q < 16; ++q) printf(" %.0f", by_warp_first[q]);
+    for (unsigned q = 0; q < WPC; ++q) printf(" %.0f", by_warp_first[q]);
     printf("\n");
   }
   return 0;
