@@ -292,7 +292,10 @@ __device__ __forceinline__ void finish_and_store(const StepParams& p, const Boar
     w = words_from_pair(philox2x32_10_keys(p.env_lo + i, p.keys));
   }
   uint4 bd;
-  const StepOut o = finish_step<(G2048_PAIR_LUT && !G2048_TMA)>(lut, m, w, p.max_tile_exp, has<OUT, O_HIGHEST>(p.highest_exp),
+#ifndef G2048_FORCE_PLAIN     // experiment: max_tile = None and auto-reset as compile-time facts (what a PLAIN flavour would save)
+#define G2048_FORCE_PLAIN 0
+#endif
+  const StepOut o = finish_step<(G2048_PAIR_LUT && !G2048_TMA)>(lut, m, w, G2048_FORCE_PLAIN ? 0u : p.max_tile_exp, has<OUT, O_HIGHEST>(p.highest_exp),
                                                     auto_reset, bd.x, bd.y, bd.z, bd.w);
   const float reward = o.legal ? o.score : p.illegal_move_reward;                        // :90 / :95
   p.boards_out[i] = bd;
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
 #else
   const Board4* lut = make_reset_lut(s_lut);
 #endif
-  const bool auto_reset = (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
+  const bool auto_reset = G2048_FORCE_PLAIN ? true : (p.flags & G2048_FLAG_AUTO_RESET) != 0u;
   const uint32_t n = p.n;
 #if !G2048_TMA
   const uint32_t stride = gridDim.x * blockDim.x;               // the CTA width is chosen at launch (shape_for)
