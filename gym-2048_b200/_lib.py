@@ -17,9 +17,12 @@ HEADERS = [os.path.join(_PKG, "csrc", "g2048_device.cuh"), os.path.join(_PKG, "c
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_AUTO_RESET = 1
 FLAG_POLICY_UNIFORM, FLAG_POLICY_LEGAL = 2, 4
+FLAG_CHAIN_INTERLEAVED = 16  # G2048_FLAG_CHAIN_INTERLEAVED: launches of other chains in between (launch shape)
+FLAG_CHAINED = 8            # G2048_FLAG_CHAINED: per-slice dependency on the previous launch of the same chain buffer
+CHAIN_WORDS = 16384          # G2048_CHAIN_WORDS (64-bit words of a chain buffer)
 OBS_U8, OBS_F32, OBS_I64, OBS_BF16 = 0, 1, 2, 3
 
 EXPORTS = [
@@ -50,7 +53,7 @@ class StepArgs(C.Structure):
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
         ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
-        ("boards_nibble", C.c_void_p), ("nibble_overflow", C.c_void_p),
+        ("boards_nibble", C.c_void_p), ("nibble_overflow", C.c_void_p), ("chain", C.c_void_p),
     ]
 
 

@@ -106,6 +106,9 @@ class BatchedGame2048:
         self.final_return = torch.zeros(n, dtype=torch.float32, device=dev) if ep else None
         self._step_counter = None      # device uint64 step index (use_device_step_counter)
         self._actions_out = None       # where step(policy=...) writes the actions it drew
+        self._chain = None             # chain buffer of chained launches (step(chained=True), step_n, StepSchedule)
+        self._chain_broken = True      # the next step must not chain: something else wrote the env's state
+        self._chain_mode = "direct"    # launch shape of the env's chain: "direct" or "interleaved"
         self._args = None              # cached G2048StepArgs, rebuilt when a knob changes
 
     # -- knobs (reference :61-73) ------------------------------------------------------
@@ -161,6 +164,7 @@ class BatchedGame2048:
             if self._step_counter is not None:
                 self._step_counter.zero_()
         m = None if mask is None else self._as_u8(mask, (self.num_envs,), "mask")
+        self._chain_broken = True
         self._launch(self.lib.g2048_reset, self._ptr(self.boards), self._ptr(m), self.num_envs, self.env_id_base,
                      self.seed, self.reset_index)
         self.reset_index += 1
@@ -196,14 +200,53 @@ class BatchedGame2048:
                                   self.highest_exp, self.legal_mask, self.terminal_boards, self.final_score,
                                   self.final_len, self.final_return)
 
+    def _chain_args(self, a, chained):
+        """Chained launches (G2048StepArgs.chain / G2048_FLAG_CHAINED) for the step call `a`; chained = False, True or
+        "interleaved" (see step()).  The env's chain buffer is made (zeroed) at the first chained step; from then on
+        EVERY step launch of this env carries it, chained or not — the kernel publishes the finished warps of every
+        launch, so the next one may chain to it.  A step that follows anything else this class did to the env's
+        state (reset, set_boards, step_many, ...), or that changes between direct and interleaved chaining (another
+        launch shape), is issued unchained whatever the caller promised."""
+        if chained not in (False, True, "interleaved"):
+            raise ValueError("chained must be False, True or 'interleaved'")
+        if chained and self._chain is None:
+            if self._step_counter is not None:
+                raise G2048Error("chained steps are not available with a device-side step counter")
+            self._chain = torch.zeros(_lib.CHAIN_WORDS, dtype=torch.int64, device=self.device)
+            self._chain_broken = True
+        if self._chain is None or self._step_counter is not None:
+            a.chain = None
+            self._chain_broken = True          # a launch outside the protocol: the next chained step starts a new chain
+            return
+        a.chain = self._chain.data_ptr()
+        mode = "interleaved" if chained == "interleaved" else "direct"
+        if not chained:
+            mode = self._chain_mode             # an unchained step in between keeps the chain's shape
+        if mode == "interleaved":
+            a.flags |= _lib.FLAG_CHAIN_INTERLEAVED
+        if chained and not self._chain_broken and mode == self._chain_mode:
+            a.flags |= _lib.FLAG_CHAINED
+        self._chain_broken = False
+        self._chain_mode = mode
+
     def _check_board_buffer(self, t, what):
         if not (isinstance(t, torch.Tensor) and t.dtype == torch.uint8 and t.device == self.device
                 and t.is_contiguous() and tuple(t.shape) == (self.num_envs, 16)):
             raise ValueError("%s must be a contiguous uint8 [%d,16] tensor on %s" % (what, self.num_envs, self.device))
         return t
 
-    def step(self, actions=None, forced_draws=None, boards_out=None, terminal_out=None, policy=None):
+    def step(self, actions=None, forced_draws=None, boards_out=None, terminal_out=None, policy=None, chained=False):
         """One env step for every board.  `actions`: uint8/int tensor [n] on any device.
+
+        chained=True / "interleaved" (G2048_FLAG_CHAINED, include/g2048.h): the caller's promise that everything this
+        step reads — the boards, `actions` (or the legal mask with policy='legal'), the episode statistics — was
+        last written by THIS env's previous step() or before that step was issued: open-loop action rows prepared
+        in advance, the in-kernel policies, several envs stepped round-robin.  The launch then depends on its
+        predecessor warp by warp instead of waiting for the whole grid to drain, with identical results.  True: this
+        env is stepped back to back (1 Mi boards 10.5 -> 9.4 us per step, 262,144 4.1 -> 3.6 us); "interleaved":
+        steps of OTHER envs sit between two steps of this one (several env sets round-robin: 10.8 -> 9.05 us and
+        4.4 -> 2.5 us).  Leave it False when a policy kernel wrote `actions` after the previous step (a closed
+        loop), or after touching the env's tensors directly.
 
         policy = "uniform" / "legal": the kernel draws the actions itself — exactly the actions sample_actions(legal=...)
         would return for this step — and steps with them in the SAME launch (BASELINE config 4: sample a legal action,
@@ -252,6 +295,7 @@ class BatchedGame2048:
         a.step_index = self.step_index
         a.boards = self.boards.data_ptr()
         a.flags = (FLAG_AUTO_RESET if self.auto_reset else 0) | pol
+        self._chain_args(a, chained)
         a.boards_out = None if boards_out is None else self._check_board_buffer(boards_out, "boards_out").data_ptr()
         # every per-call pointer of the cached struct is reassigned on every call: a stale terminal_out would
         # keep the kernel writing into a buffer its owner (e.g. a dropped TransitionRecorder) may have freed
@@ -277,14 +321,18 @@ class BatchedGame2048:
         res.actions = act
         return res
 
-    def step_n(self, actions, rewards=None, dones=None, illegal=None, highest_exp=None, legal_mask_out=None):
+    def step_n(self, actions, rewards=None, dones=None, illegal=None, highest_exp=None, legal_mask_out=None,
+               chained=True):
         """K consecutive steps, ONE KERNEL LAUNCH PER STEP, issued back to back from C (g2048_step_n): what
         `for k in range(K): step(actions[k])` does — every step reads and writes the boards in device memory —
         without the interpreter between two launches (a Python loop issues a launch every ~6 us, a B200 steps
         131,072 boards in ~3 us).  `actions`: contiguous uint8 [K,n] on the device (an open-loop sequence).
         Returns (rewards f32 [K,n], dones bool [K,n]); `illegal`, `highest_exp`, `legal_mask_out` (uint8 [K,n])
         are filled when given.  The env's running episode statistics (ep_score/ep_len/ep_return) are kept;
-        terminal boards and final_* of the intermediate steps are not reported (use step() for those)."""
+        terminal boards and final_* of the intermediate steps are not reported (use step() for those).
+        chained (default): steps 2..K are chained launches (see step()) — every action row was there before the
+        call, so step k+1 only depends on step k, slice by slice; the first step waits for all earlier work on the
+        stream as any launch does."""
         n = self.num_envs
         if self._step_counter is not None:
             raise G2048Error("step_n is not available with a device-side step counter")
@@ -315,6 +363,8 @@ class BatchedGame2048:
                      n, self.env_id_base, self.seed, self.step_index,
                      self.illegal_move_reward, self.max_tile_exp, FLAG_AUTO_RESET if self.auto_reset else 0, None,
                      self._ptr(self.ep_return), None)
+        if chained:
+            self._chain_args(a, True)          # (the C loop sets the flag itself from the second step on)
         self._launch(self.lib.g2048_step_n, C.byref(a), K, n)
         self.step_index += K
         if self.legal_mask is not None:
@@ -415,6 +465,7 @@ class BatchedGame2048:
                          K, self.illegal_move_reward, self.max_tile_exp, flags, self._ptr(actions_out),
                          self._ptr(legal_mask_out))
         if K:
+            self._chain_broken = True
             self._launch(self.lib.g2048_step_many, C.byref(a))
             self.step_index += K
             if self.legal_mask is not None:
@@ -456,6 +507,7 @@ class BatchedGame2048:
         d = self._as_u8(directions, (self.num_envs,), "actions")
         scores = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         changed = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._chain_broken = self._chain_broken or not trial
         self._launch(self.lib.g2048_move, self._ptr(self.boards), None if trial else self._ptr(self.boards),
                      self._ptr(d), self._ptr(scores), self._ptr(changed), self.num_envs)
         return scores, changed.view(torch.bool)
@@ -499,6 +551,7 @@ class BatchedGame2048:
         if v.numel() != self.num_envs * 16:
             raise ValueError("expected %d cells, got %d" % (self.num_envs * 16, v.numel()))
         bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._chain_broken = True
         self._launch(self.lib.g2048_exp_from_values, self._ptr(v), self._ptr(self.boards), v.numel(), self._ptr(bad))
         if int(bad.item()):
             raise ValueError("%d cells are not 0 or a power of two in 2..2^31" % int(bad.item()))
@@ -506,6 +559,7 @@ class BatchedGame2048:
             self.status(legal_mask=self.legal_mask)
 
     def set_boards(self, exps):
+        self._chain_broken = True
         self.boards.copy_(self._as_u8(exps, (self.num_envs, 16), "boards"))
         if self.legal_mask is not None:
             self.status(legal_mask=self.legal_mask)
@@ -521,6 +575,7 @@ class BatchedGame2048:
         return sd
 
     def load_state_dict(self, sd):
+        self._chain_broken = True
         self.boards.copy_(sd["boards"])
         self.seed, self.step_index, self.reset_index = int(sd["seed"]), int(sd["step_index"]), int(sd["reset_index"])
         self.env_id_base = int(sd["env_id_base"])
@@ -679,9 +734,10 @@ class StepSchedule:
     def __len__(self):
         return len(self._items)
 
-    def add(self, game, actions=None, policy=None):
+    def add(self, game, actions=None, policy=None, chained=False):
         """Record game.step(actions) — or game.step(policy=...), the actions then being drawn by the kernel and written
-        to `actions` (or the game's internal buffer)."""
+        to `actions` (or the game's internal buffer).  chained: as in BatchedGame2048.step (the action rows of a
+        schedule exist before it runs, so a schedule that is the only thing stepping its games may chain them all)."""
         n = game.num_envs
         pol = 0
         if policy is not None:
@@ -711,6 +767,7 @@ class StepSchedule:
         a.step_index = game.step_index
         a.boards = game.boards.data_ptr()
         a.flags = (FLAG_AUTO_RESET if game.auto_reset else 0) | pol
+        game._chain_args(a, chained)
         game.step_index += 1
         self._items.append(a)
         self._keep.append((game, actions))

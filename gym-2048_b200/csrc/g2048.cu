@@ -66,6 +66,18 @@ int cuda_fail(cudaError_t e, const char* what) {
 #ifndef G2048_STAGES
 #define G2048_STAGES 4
 #endif
+#ifndef G2048_NOWAIT         // EXPERIMENT ONLY: the step kernel skips griddepcontrol.wait — no ordering against the previous
+#define G2048_NOWAIT 0       // launch at all (wrong in general); measures what a finer-grained dependency could gain
+#endif
+#ifndef G2048_CHAIN_NO_LATE_WAIT   // EXPERIMENT ONLY: chained launches never wait for the previous grid (breaks the stream
+#define G2048_CHAIN_NO_LATE_WAIT 0 // order for whatever follows them); measures what the wait at their end costs
+#endif
+#ifndef G2048_LUT_WAIT_EARLY // 1: wait for the fresh-board table copy before the first board is loaded (round 2's order)
+#define G2048_LUT_WAIT_EARLY 0
+#endif
+#ifndef G2048_LUT_GLOBAL     // EXPERIMENT: the 16 KB fresh-board table is read from global memory (L1-cached) instead of a
+#define G2048_LUT_GLOBAL 0   // per-CTA shared-memory copy
+#endif
 constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 // The step kernels' own persistent shape.  One 1024-thread CTA per SM measured 1 % faster than two of 512
 // (12.23 vs 12.37 us per 1 Mi boards): with two CTAs the hardware scheduler favours the older one and the SM
@@ -166,6 +178,24 @@ static bool first_use_on_current_device(uint64_t& seen) {
 // ------------------------------------------------------------------------------------
 constexpr uint32_t kFlagBumpCounter = 0x80000000u;   // internal: this launch advances *step_counter when it ends
 constexpr uint32_t kFlagPrefetch = 0x40000000u;      // internal: L2-prefetch the first boards before griddepcontrol.wait
+constexpr uint32_t kFlagChained = 0x20000000u;       // internal: G2048_FLAG_CHAINED — the launch waits per slice, not per grid
+// Chain buffer (G2048StepArgs.chain, G2048_CHAIN_WORDS 64-bit words): one word per WARP of a chained launch shape
+// (kChainSlices CTAs of kChainThreads threads at most) = the step index + 1 of the last launch whose warp there is done.
+#ifndef G2048_CHAIN_THREADS          // launch shape of a step that carries a chain buffer (experiments: scripts/chain_variants.sh)
+#define G2048_CHAIN_THREADS 256
+#endif
+#ifndef G2048_CHAIN_CTAS_PER_SM           // a chain whose launches follow each other directly (every launch waits for its
+#define G2048_CHAIN_CTAS_PER_SM 4         // predecessor's warps): a wide launch, the fifth place on an SM is for the next one
+#endif
+#ifndef G2048_CHAIN_NARROW_CTAS_PER_SM    // G2048_FLAG_CHAIN_INTERLEAVED: launches of other chains in between — several
+#define G2048_CHAIN_NARROW_CTAS_PER_SM 1  // launches share the machine side by side, each one CTA per SM
+#endif
+constexpr unsigned kChainThreads = G2048_CHAIN_THREADS, kChainCtasPerSm = G2048_CHAIN_CTAS_PER_SM,
+                   kChainNarrowCtasPerSm = G2048_CHAIN_NARROW_CTAS_PER_SM;
+// (a call whose env ids cross a multiple of 2^32 is two launches: the second one uses the upper half of the buffer)
+constexpr unsigned kChainLaunchWords = G2048_CHAIN_WORDS / 2u;
+constexpr unsigned kChainSlices = kChainLaunchWords / (kChainThreads / 32u);     // CTAs a launch has words for
+static_assert(kChainThreads % 32u == 0u && kChainThreads <= 1024u && kChainSlices >= 148u * kChainCtasPerSm, "chain shape");
 #ifndef G2048_PREFETCH_MIN_N   // the prologue prefetch pays from this batch size on (3.47 -> 3.16 us WITHOUT it at 131,072
 #define G2048_PREFETCH_MIN_N 200000   // boards, 4.74 -> 4.24 us with it at 262,144, 11.5 -> 11.0 us at 1 Mi; profiles/r02_variants.log)
 #endif
@@ -190,6 +220,8 @@ struct StepParams {
   uint32_t* nibble_overflow;    // counter of boards whose exponents do not fit 4 bits (a tile >= 65,536)
   const uint4* forced_draws;
   uint64_t* step_counter;       // [0] step index, [1] CTA arrival ticket (0 between launches)
+  unsigned long long* chain;    // fine-grained dependency between consecutive launches over the same boards (see the kernel)
+  unsigned long long chain_tag; // step index + 1: what a warp publishes when it is done; a chained warp waits for chain_tag - 1
   uint32_t n;                   // < 2^32 - 256 (checked by the host)
   uint32_t env_lo;              // low half of the env id of board 0; the launch never crosses 2^32
   uint32_t env_hi;              // high half, the same for every board
@@ -396,7 +428,9 @@ template <uint32_t OUT, bool COUNTER, int POLICY = 0>
 __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kernel(const StepParams p) {
   static_assert(POLICY == 0 || (!G2048_TMA && !G2048_PIPELINE), "the policy kernels exist for the plain loop only");
   static_assert(POLICY != 2 || (OUT & (O_MASK | O_GENERIC)) != 0u, "the random-legal policy reads and writes the legal mask");
-#if G2048_PAIR_LUT && !G2048_TMA
+#if G2048_LUT_GLOBAL
+  // (experiment) the fresh-board table is read where it lies, through the L1: no per-CTA copy, no barrier
+#elif G2048_PAIR_LUT && !G2048_TMA
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
   if (threadIdx.x == 0) {
@@ -419,6 +453,24 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #endif
+  // ---- chained launches (G2048StepArgs.chain) ----------------------------------------------------------------
+  // A step over boards that the PREVIOUS step launch wrote depends on that launch board by board, not grid by grid:
+  // thread t of CTA b owns the same boards in every launch of the same shape.  With a chain buffer every warp
+  // publishes "step index + 1" in its own word when its last store is out (release at GPU scope), and a launch that
+  // carries kFlagChained does not wait for the previous GRID (griddepcontrol.wait) but, warp by warp, for that word
+  // to show the previous step (acquire).  The launches are programmatic dependent launches whose CTAs signal
+  // launch_dependents at entry, so the hardware starts a CTA of the next launch as soon as an SM has room for it:
+  // its prologue runs in the shadow of the CTAs still at work there, and there is no grid-wide drain, release
+  // and ramp between two steps (2.35 us of an 11 us launch over 1 Mi boards).  No deadlock: a CTA of launch k+1
+  // exists only after every CTA of launch k has started.  A launch WITHOUT the flag (the head of a chain, or a
+  // step after foreign work touched its inputs) keeps griddepcontrol.wait; it still publishes.
+  const bool chain = p.chain != nullptr;
+  const bool chained = chain && (p.flags & kFlagChained) != 0u;
+  // (the first look at the warp's word is taken right here, so that its round trip to the L2 overlaps the prologue)
+  const unsigned long long* const chain_word = p.chain + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  unsigned long long chain_seen = 0ull;
+  if (chained && (threadIdx.x & 31u) == 0u)
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(chain_seen) : "l"(chain_word) : "memory");
 #if G2048_PDL
   // Let the next launch in the stream start its ramp as soon as our CTAs retire; everything
   // before griddepcontrol.wait touches no global memory a previous launch could have written (only the
@@ -429,7 +481,10 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     const uint32_t k = threadIdx.x - 32;
     s_sel[k] = (k < 4) ? kOrientIn[k] : kOrientOut[k - 4];
   }
-#if G2048_PAIR_LUT && !G2048_TMA
+#if G2048_LUT_GLOBAL
+  __syncthreads();                          // s_sel written
+  const Board4* lut = g_pair_lut.e;
+#elif G2048_PAIR_LUT && !G2048_TMA
   __syncthreads();                          // s_sel written, s_lut_bar initialised
   const Board4* lut = s_lut;
 #else
@@ -452,10 +507,23 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
       asm volatile("prefetch.global.L2 [%0];" ::"l"((POLICY == 2 ? p.legal_mask : p.actions) + i));
   }
 #endif
-#if G2048_PDL
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if G2048_PDL && !G2048_NOWAIT
+  if (chained) {
+    if ((threadIdx.x & 31u) == 0u) {
+      const unsigned long long want = p.chain_tag - 1ull;      // what this warp's predecessor published
+      uint32_t polls = 0u;
+      while (chain_seen != want) {
+        if (++polls > 16u) __nanosleep(64);
+        if (polls > (1u << 21)) __trap();                      // > 1 s: the caller chained to a launch that never ran
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(chain_seen) : "l"(chain_word) : "memory");
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 #endif
-#if G2048_PAIR_LUT && !G2048_TMA
+#if G2048_PAIR_LUT && !G2048_TMA && !G2048_LUT_GLOBAL && (G2048_PIPELINE || G2048_LUT_WAIT_EARLY)
   mbar_wait(&s_lut_bar, 0u);                // the table copy was started in the prologue; long done by now
 #endif
   uint64_t counter_value = 0;
@@ -469,7 +537,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     __syncthreads();                        // every thread of the CTA has read the index before thread 0 can arrive
   }
 #if !G2048_TMA
-  if (i >= n) return;
+  if (i >= n && !chain) return;             // (a chained warp stays whole: it publishes after its last store)
 #endif
   // Grid-stride loop, software-pipelined one board ahead.  orient() consumes the loaded board
   // right away, so the next board is prefetched into the same registers (no rotation copies)
@@ -567,6 +635,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     finish_and_store<OUT, COUNTER>(p, lut, i, m, dev_key, dev_idx_lo, auto_reset, load_episode<OUT>(p, i));
   }
 #else
+  if (i < n) {
   const uint4* pb = p.boards + i;
   // the byte prefetched next to the board: the action, or (random-legal policy) the board's legal mask
   const uint8_t* const side = POLICY == 2 ? p.legal_mask : p.actions;
@@ -574,6 +643,12 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
   uint4 bd = load_board(pb);
   uint32_t action = POLICY == 1 ? 15u : *pa;
   EpIn ep_next = load_episode<OUT>(p, i);
+#if G2048_PAIR_LUT && !G2048_LUT_GLOBAL && !G2048_LUT_WAIT_EARLY
+  // The fresh-board table (its copy was started in the prologue) is first read at the end of a step: wait for it
+  // with the first board's load already in flight.  (A chained CTA starts working as soon as it is resident: its
+  // table copy is not "long done" as it is behind griddepcontrol.wait.)
+  mbar_wait(&s_lut_bar, 0u);
+#endif
 #if G2048_STAGGER
   // Experiment: the eight warps of an SM sub-partition run the same instruction stream in near lockstep — all in
   // the ALU-heavy move, then all in the FMA-heavy Philox/spawn — so the two pipes take turns idling.  Start them
@@ -622,6 +697,22 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     ep_next = load_episode<OUT>(p, i_next);
 #endif
     i = i_next;
+  }
+  }
+  if (chain) {
+    // Publish: the warp's stores are ordered before lane 0's release store by the warp barrier, and the release
+    // makes them visible at GPU scope before the word.
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0u)
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(const_cast<unsigned long long*>(chain_word)), "l"(p.chain_tag) : "memory");
+#if G2048_PDL && !G2048_NOWAIT && !G2048_CHAIN_NO_LATE_WAIT
+    // A chained launch did not wait for the previous grid before its work — it waits for it now, before it ENDS.
+    // Stream order is transitive only through kernels that wait: a kernel behind this one (a plain step of another
+    // env set, any programmatic dependent launch) waits for THIS grid to complete and must be able to conclude that
+    // everything issued before it has completed too.  The launch in front of us started earlier and is normally
+    // done by now; the words above are already published, so no successor is held up.
+    if (chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   }
 #endif
   // The last CTA to arrive advances the device-side step index: by then every CTA has read it.
@@ -1171,6 +1262,8 @@ static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepPara
   p.nibble_overflow = a->nibble_overflow;
   p.forced_draws = reinterpret_cast<const uint4*>(a->forced_draws);
   p.step_counter = a->step_counter;
+  p.chain = reinterpret_cast<unsigned long long*>(a->chain);
+  p.chain_tag = a->step_index + 1ull;
   p.n = (uint32_t)a->n;
   p.env_lo = (uint32_t)a->env_id_base;
   p.env_hi = (uint32_t)(a->env_id_base >> 32);
@@ -1181,14 +1274,30 @@ static void fill_step_params(const G2048StepArgs* a, bool bump_counter, StepPara
   p.actions_out = const_cast<uint8_t*>(a->actions);
   p.illegal_move_reward = a->illegal_move_reward;
   p.max_tile_exp = a->max_tile_exp;
-  p.flags = (a->flags & ~(kFlagBumpCounter | kFlagPrefetch)) | (bump_counter ? kFlagBumpCounter : 0u) |
-            (a->n >= G2048_PREFETCH_MIN_N ? kFlagPrefetch : 0u);
+  p.flags = (a->flags & ~(kFlagBumpCounter | kFlagPrefetch | kFlagChained | G2048_FLAG_CHAINED | G2048_FLAG_CHAIN_INTERLEAVED)) |
+            (bump_counter ? kFlagBumpCounter : 0u) | (a->n >= G2048_PREFETCH_MIN_N ? kFlagPrefetch : 0u) |
+            (a->chain && (a->flags & G2048_FLAG_CHAINED) && a->step_index != 0 ? kFlagChained : 0u);
 }
 
 // Launch configuration of a step over n boards (shape_for), with the kernel attributes it relies on set once per
 // device and host thread.
-static void step_launch_config(uint64_t n, cudaStream_t s, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+// chain: 0 = no chain buffer, 1 = chain buffer, 2 = chain buffer + G2048_FLAG_CHAIN_INTERLEAVED
+static void step_launch_config(uint64_t n, int chain, cudaStream_t s, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
   std::memset(&cfg, 0, sizeof cfg);
+  if (chain) {
+    // Launches that carry a chain buffer overlap on an SM: 256-thread CTAs (five fit an SM at 48 registers).
+    //   a chain stepped back to back: four CTAs per SM — only ONE launch is at work at a time (its successor's
+    //     warps wait), so the launch itself must fill the SM; the fifth place is where a CTA of the next launch
+    //     runs its prologue and waits (1 Mi boards 10.5 -> 9.4 us, 262,144 4.1 -> 3.6 us);
+    //   interleaved chains (several env sets round-robin): one CTA per SM — consecutive launches are independent,
+    //     five of them share an SM side by side and every CTA lives four times as long, which amortises its start
+    //     and its end (1 Mi boards 10.8 -> 9.05 us, 262,144 4.4 -> 2.5 us; profiles/r02_chain_shapes.log).
+    const uint64_t need = (n + kChainThreads - 1) / kChainThreads;
+    uint64_t cap = (uint64_t)sm_count() * (chain == 2 ? kChainNarrowCtasPerSm : kChainCtasPerSm);
+    if (cap > kChainSlices) cap = kChainSlices;
+    cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
+    cfg.blockDim = dim3(kChainThreads);
+  } else {
 #if G2048_TMA || !G2048_PAIR_LUT
   {
     const uint64_t need = (n + kStepThreads - 1) / kStepThreads, cap = (uint64_t)sm_count() * kStepCtasPerSm;
@@ -1204,6 +1313,7 @@ static void step_launch_config(uint64_t n, cudaStream_t s, cudaLaunchConfig_t& c
   cfg.gridDim = dim3((unsigned)((n + kStepThreads - 1) / kStepThreads));
   cfg.blockDim = dim3(kStepThreads);
 #endif
+  }
   {
     static thread_local uint64_t seen = 0;
     if (first_use_on_current_device(seen)) {           // once per device and thread: allow the padding, prefer shared memory
@@ -1234,7 +1344,7 @@ static int launch_step(const G2048StepArgs* a, cudaStream_t s, bool bump_counter
   fill_step_params(a, bump_counter, p);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  step_launch_config(a->n, s, cfg, attr);
+  step_launch_config(a->n, a->chain ? ((a->flags & G2048_FLAG_CHAIN_INTERLEAVED) ? 2 : 1) : 0, s, cfg, attr);
   void* kargs[] = {&p};
   const void* kernel = pick_step_kernel(a);
   if (!kernel) return fail(G2048_ERR_INVALID, "g2048_step: this build has no kernel for the requested policy flag");
@@ -1254,8 +1364,17 @@ static int check_step_args(const G2048StepArgs* a, const char* fn) {
   if (reinterpret_cast<uintptr_t>(a->boards_nibble) & 7u)
     return fail(G2048_ERR_ALIGN, "%s: boards_nibble must be 8-byte aligned", fn);
   if (a->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "%s: max_tile_exp %u > 63", fn, a->max_tile_exp);
-  if (a->flags & ~(G2048_FLAG_AUTO_RESET | G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL))
+  if (a->flags & ~(G2048_FLAG_AUTO_RESET | G2048_FLAG_POLICY_UNIFORM | G2048_FLAG_POLICY_LEGAL | G2048_FLAG_CHAINED |
+                   G2048_FLAG_CHAIN_INTERLEAVED))
     return fail(G2048_ERR_INVALID, "%s: unknown flags 0x%x", fn, a->flags);
+  if ((a->flags & (G2048_FLAG_CHAINED | G2048_FLAG_CHAIN_INTERLEAVED)) && !a->chain)
+    return fail(G2048_ERR_INVALID, "%s: G2048_FLAG_CHAINED / G2048_FLAG_CHAIN_INTERLEAVED need the chain buffer", fn);
+  if (a->chain && a->step_counter)
+    return fail(G2048_ERR_INVALID, "%s: chain and step_counter cannot be combined", fn);
+  if (reinterpret_cast<uintptr_t>(a->chain) & 7u)
+    return fail(G2048_ERR_ALIGN, "%s: chain must be 8-byte aligned", fn);
+  if (a->chain && (G2048_TMA || G2048_PIPELINE))
+    return fail(G2048_ERR_INVALID, "%s: this build variant has no chained launches", fn);
   if ((a->flags & G2048_FLAG_POLICY_UNIFORM) && (a->flags & G2048_FLAG_POLICY_LEGAL))
     return fail(G2048_ERR_INVALID, "%s: choose one of G2048_FLAG_POLICY_UNIFORM / G2048_FLAG_POLICY_LEGAL", fn);
   if ((a->flags & G2048_FLAG_POLICY_LEGAL) && !a->legal_mask)
@@ -1271,7 +1390,9 @@ static int check_step_args(const G2048StepArgs* a, const char* fn) {
 static int issue_step(const G2048StepArgs* a, cudaStream_t s) {
   const uint64_t to_boundary = 0x100000000ull - (a->env_id_base & 0xFFFFFFFFull);
   if (a->n > to_boundary) {
-    const G2048StepArgs first = slice_args(*a, 0, to_boundary), second = slice_args(*a, to_boundary, a->n - to_boundary);
+    const G2048StepArgs first = slice_args(*a, 0, to_boundary);
+    G2048StepArgs second = slice_args(*a, to_boundary, a->n - to_boundary);
+    if (second.chain) second.chain += kChainLaunchWords;      // each half chains to the same half of the previous call
     const int rc = launch_step(&first, s, false);
     return rc == G2048_OK ? launch_step(&second, s, true) : rc;     // both read the index, the second advances it
   }
@@ -1315,6 +1436,7 @@ int g2048_step_n(const G2048StepArgs* a, uint32_t n_steps, uint64_t row_stride, 
     if (k.forced_draws) k.forced_draws += 4 * row_stride;
     if (k.boards_nibble) k.boards_nibble += 8 * row_stride;
     k.step_index += 1;
+    if (k.chain) k.flags |= G2048_FLAG_CHAINED;       // step t+1 reads what step t wrote and rows that were there before the call
   }
   return launch_check("g2048_step_kernel");
 }

@@ -52,11 +52,12 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 4 /* 2: G2048StepArgs.boards_out, data-side entry points */
+#define G2048_ABI_VERSION 5 /* 2: G2048StepArgs.boards_out, data-side entry points */
                             /* 3: draw stream version 2, g2048_philox2x32, g2048_draw_words, */
                             /*    g2048_step_many                                            */
                             /* 4: G2048StepArgs.ep_return/final_return, g2048_step_n,        */
                             /*    g2048_one (single-env packed call)                         */
+                            /* 5: G2048StepArgs.chain, G2048_FLAG_CHAINED (chained launches)  */
 
 #define G2048_TAG_STEP   0u
 #define G2048_TAG_RESET  1u
@@ -75,6 +76,35 @@ extern "C" {
 /* policy itself and WRITES the action it drew (g2048_step: into `actions`)                */
 #define G2048_FLAG_POLICY_UNIFORM 2u /* action uniform in {0,1,2,3} (train.py:119)        */
 #define G2048_FLAG_POLICY_LEGAL   4u /* uniform among the legal moves of the live board   */
+/*
+ * Chained launches (G2048StepArgs.chain).  Consecutive steps of the SAME boards depend on each other board by
+ * board; a kernel launch normally waits for the whole previous launch to drain (~2.3 us of an ~11 us step over
+ * 1 Mi boards).  With a chain buffer every warp of the step kernel publishes "step_index + 1" in its own word of
+ * `chain` when it is done, and a launch that carries G2048_FLAG_CHAINED waits warp by warp for the step
+ * step_index - 1 instead of for the grid: its CTAs start as soon as an SM has room for them.  Results are
+ * bit-identical to unchained launches (tests/test_gpu_chain.py).
+ *   chain  device memory, G2048_CHAIN_BYTES, 8-byte aligned, ZEROED before its first use and whenever n changes;
+ *          one buffer per env set (per `boards`), used on one stream.  Every launch that carries it — chained or
+ *          not — publishes, so chained and plain launches of a set can be mixed freely.
+ *   G2048_FLAG_CHAINED  the caller's promise about THIS launch: the previous launch that carried this chain
+ *          buffer had the same n and step_index - 1, and everything this launch reads (boards, actions or — with
+ *          G2048_FLAG_POLICY_LEGAL — legal_mask, the running episode statistics, forced_draws) was last written
+ *          either by that launch or before it was issued.  Open-loop action sequences (g2048_step_n sets the
+ *          flag itself from the second step on), the in-kernel policies, round-robin stepping of several env
+ *          sets.  NOT a closed loop in which a policy kernel writes this step's actions after the previous step:
+ *          leave the flag off there — the launch then waits for all earlier work on the stream as usual.  A
+ *          launch with step_index 0 is never chained.  Not combinable with step_counter.
+ *   G2048_FLAG_CHAIN_INTERLEAVED  how the chain is used, which decides the launch shape (a chained launch must
+ *          carry the same value as the launch it chains to; change it with an unchained launch).  Clear: the
+ *          launches of this chain follow each other directly on the stream (g2048_step_n, one env set stepped
+ *          in a loop) — every launch fills the machine.  Set: launches of OTHER chains sit in between (several
+ *          env sets stepped round-robin) — a launch takes a fifth of every SM and up to five consecutive launches
+ *          run side by side.  A wrong choice costs time, not correctness.
+ */
+#define G2048_FLAG_CHAINED 8u
+#define G2048_FLAG_CHAIN_INTERLEAVED 16u
+#define G2048_CHAIN_WORDS 16384u                   /* 64-bit words */
+#define G2048_CHAIN_BYTES (8u * G2048_CHAIN_WORDS)
 
 /* g2048_encode_obs dtype */
 #define G2048_OBS_U8   0
@@ -141,6 +171,8 @@ typedef struct G2048StepArgs {
                                    /*        <= 32768); 8-byte aligned                     */
   uint32_t*       nibble_overflow; /* device uint32, nullable: incremented once per board  */
                                    /*        whose exponents do not fit (a tile >= 65536)  */
+  uint64_t*       chain;           /* device, G2048_CHAIN_BYTES, nullable: chained launches */
+                                   /*        (G2048_FLAG_CHAINED above)                     */
 } G2048StepArgs;
 
 int g2048_abi_version(void);

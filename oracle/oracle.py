@@ -25,6 +25,7 @@ class StepArgs(C.Structure):
         ("flags", C.c_uint32), ("boards_out", C.c_void_p),
         ("ep_return", C.c_void_p), ("final_return", C.c_void_p),
         ("boards_nibble", C.c_void_p), ("nibble_overflow", C.c_void_p),
+        ("chain", C.c_void_p),          # a launch-scheduling device buffer of the CUDA library; the oracle ignores it
     ]
 
 

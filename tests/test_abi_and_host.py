@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), name
     assert sorted(g._lib.EXPORTS) == names
-    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 4
+    assert L.g2048_abi_version() == g._lib.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():
@@ -45,8 +45,8 @@ def test_struct_layouts_match_header():
       printf("%zu %zu %zu %zu %zu\n", offsetof(G2048StepArgs, boards_out), offsetof(G2048StepArgs, ep_return),
              offsetof(G2048StepArgs, final_return), sizeof(G2048OneIO), offsetof(G2048OneIO, reward));
       printf("%zu %zu\n", offsetof(G2048OneIO, done), offsetof(G2048OneIO, bad_cells));
-      printf("%zu %zu %zu\n", offsetof(G2048StepArgs, boards_nibble), offsetof(G2048StepArgs, nibble_overflow),
-             offsetof(G2048EnvConfig, board_format));
+      printf("%zu %zu %zu %zu %u\n", offsetof(G2048StepArgs, boards_nibble), offsetof(G2048StepArgs, nibble_overflow),
+             offsetof(G2048EnvConfig, board_format), offsetof(G2048StepArgs, chain), G2048_CHAIN_WORDS);
       return 0;
     }'''
     d = os.path.join(ROOT, "tests", "host_sim")
@@ -67,6 +67,9 @@ def test_struct_layouts_match_header():
     for S in (g._lib.StepArgs, oracle.StepArgs):
         assert [S.boards_nibble.offset, S.nibble_overflow.offset] == out[17:19]
     assert g._lib.EnvConfig.board_format.offset == out[19]
+    for S in (g._lib.StepArgs, oracle.StepArgs):
+        assert S.chain.offset == out[20]
+    assert g._lib.CHAIN_WORDS == out[21]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
@@ -130,6 +133,13 @@ def test_argument_checks_that_need_no_gpu():
     assert L.g2048_step(C.byref(a), None) == -1 and b"legal_mask" in L.g2048_last_error()
     a.flags = g._lib.FLAG_POLICY_UNIFORM | g._lib.FLAG_POLICY_LEGAL
     assert L.g2048_step(C.byref(a), None) == -1 and b"choose one" in L.g2048_last_error()
+    a.flags = g._lib.FLAG_AUTO_RESET | g._lib.FLAG_CHAINED                 # a chained launch needs the chain buffer
+    assert L.g2048_step(C.byref(a), None) == -1 and b"chain buffer" in L.g2048_last_error()
+    a.flags, a.chain = g._lib.FLAG_AUTO_RESET, fake + 4
+    assert L.g2048_step(C.byref(a), None) == -2 and b"chain must be 8-byte aligned" in L.g2048_last_error()
+    a.chain, a.step_counter = fake, fake
+    assert L.g2048_step(C.byref(a), None) == -1 and b"cannot be combined" in L.g2048_last_error()
+    a.chain, a.step_counter = None, None
     a.flags = g._lib.FLAG_AUTO_RESET
     assert L.g2048_step_n(C.byref(a), 4, 3, None) == -1 and b"row_stride" in L.g2048_last_error()
     a.step_counter = fake
