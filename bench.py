@@ -4,12 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 ours (default): one process per GPU (torchrun for N>1, NCCL only for the barrier and the
-max-over-ranks reduction — the step path has no collective).  A "step" is one call of
-BatchedGame2048.step() over one batch of `--envs` boards per GPU (default 1,048,576 =
-BASELINE config 3) with uniform-random actions; `--sets` independent batches are stepped
-round-robin so the working set exceeds the 126 MB L2.  Prints ONE JSON line with `value`
+max-over-ranks reduction — the step path has no collective).  A "step" is ONE KERNEL LAUNCH of
+g2048_step over one batch of boards — `--envs` (default 1,048,576 = BASELINE config 3) in total,
+sharded over the N ranks — with uniform-random actions; `--sets` independent batches are stepped
+round-robin so the working set exceeds the 126 MB L2.  The launches are CHAINED launches
+(include/g2048.h, G2048_FLAG_CHAINED | _CHAIN_INTERLEAVED: each depends on the previous step of its
+own env set warp by warp instead of on the whole previous grid; `--chain off` for plain ones, which
+the `plain_launches` block times anyway) issued through g2048_step_list by `--issue-threads` host
+threads (auto: two, each with its own stream and env sets).  Prints ONE JSON line with `value`
 (device-resident throughput), `e2e` (host-buffer C-ABI call, copies inside the timed
-region), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, and `fused`: the same workload through
+region), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, `long_region` (one region of
+`--long-region` launches: no event in between), and `fused`: the same workload through
 g2048_step_many (`--fused-steps` steps per launch, boards in registers in between) — an extra, not the
 headline.
 
@@ -306,28 +311,41 @@ def state_checksum(torch, dist, games, total_envs, rank, n, world, dev):
     return "%016x" % ((lo + (hi << 32)) & (2**64 - 1))
 
 
-def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, max_over_ranks_vec):
+def _add(sched, game, row, chained, policy):
+    """One launch of a schedule: game.step(row), or — policy given — game.step(policy=...) writing its actions to row."""
+    if policy:
+        sched.add(game, row, policy=policy, chained=chained)
+    else:
+        sched.add(game, row, chained=chained)
+
+
+def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, max_over_ranks_vec, chained="interleaved",
+                      policy=None):
     """Spin-up, warm-up and R back-to-back timed regions of K step launches each, round-robin over `games`.
+    chained: how every launch depends on the previous step of ITS env set (BatchedGame2048.step): "interleaved" =
+    chained launches (the action rows exist before the first launch and nothing else touches the sets, which is the
+    promise the flag makes), False = plain launches.
     Returns (region times in ms, max over ranks, per region; issue description; t_start, t_end)."""
     S, P = len(games), pool.shape[0]
     total = spinup + W + R * K
+    how = "chained launches (G2048_FLAG_CHAINED | G2048_FLAG_CHAIN_INTERLEAVED)" if chained else "plain launches"
     if small:
         # a shard the GPU steps faster than Python can launch: the whole schedule is built up front and each
         # region is ONE C call that issues its K launches (g2048_step_list)
         sched = g.StepSchedule()
         for j in range(total):
-            sched.add(games[j % S], pool[j % P])
+            _add(sched, games[j % S], pool[j % P], chained, policy)
         sched.build()
-        issue = "g2048_step_list_timed via StepSchedule (all regions in one C call; one kernel launch per env step)"
+        issue = "g2048_step_list_timed via StepSchedule (all regions in one C call; one kernel launch per env step); " + how
 
         def run(lo, hi):
             sched.run(lo, hi)
     else:
-        issue = "BatchedGame2048.step() from a Python loop (one kernel launch per env step)"
+        issue = "BatchedGame2048.step() from a Python loop (one kernel launch per env step); " + how
 
         def run(lo, hi):
             for j in range(lo, hi):
-                games[j % S].step(pool[j % P])
+                games[j % S].step(pool[j % P], chained=chained)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
     for e in ev:
         e.record()                                 # creates the cudaEvent_t handles (torch does it lazily)
@@ -354,6 +372,86 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
     barrier()
     ms = [ev[r].elapsed_time(ev[r + 1]) for r in range(R)]
     return max_over_ranks_vec(ms), issue, t_start, t_end
+
+
+def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max_over_ranks_vec, chained="interleaved",
+                         policy=None):
+    """The same launches as time_step_regions — global launch j steps env set j % S with action row j % P — issued by T
+    host threads on T streams: thread t owns the sets t, t+T, ... (a set's launches stay on one stream, in order),
+    and a timed region is K/T launches on each stream.  One host thread issues a launch every ~2.4 us on this box,
+    two ~1.4 us between them (scripts/micro/launch_cost.cu): a 131,072-board shard, which the GPU steps in ~1.3 us,
+    is otherwise timed at the speed of cudaLaunchKernelEx.  Region r's time is the slowest stream's (then the max
+    over ranks); the streams' events are staggered by half a region so that they do not drain together.
+    Returns (region times in ms; issue description; t_start, t_end; launches inside the timed regions)."""
+    S, P = len(games), pool.shape[0]
+    assert S % T == 0 and K % T == 0, "--sets and --steps must be multiples of the issuing threads"
+    total, Kt, St = spinup + W + R * K, K // T, S // T
+    dev = games[0].device
+    streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
+    scheds, starts, evs = [], [], []
+    for t in range(T):
+        sched = g.StepSchedule()
+        mine = list(range(t, S, T))                                   # this thread's env sets
+        count = {s_: (total - s_ + S - 1) // S for s_ in mine}        # launches of set s_ in the single-stream order
+        m = 0
+        while any(m < count[s_] for s_ in mine):
+            for s_ in mine:
+                if m < count[s_]:
+                    _add(sched, games[s_], pool[(s_ + m * S) % P], chained, policy)
+            m += 1
+        sched.build()
+        # region boundaries staggered by Kt/T launches from stream to stream, taken out of the spin-up (the schedule
+        # itself — how often every set is stepped — is the single-stream one: same state checksum)
+        # (and the timed regions end `tail` launches before the schedule does: a stream that is ahead of the other
+        # keeps launching while the other one is still being timed)
+        tail = max(64, 4 * Kt)
+        start = max(0, min((spinup + W) // T, len(sched) - R * Kt - tail) - ((T - 1 - t) * Kt) // T)
+        assert start + R * Kt <= len(sched)
+        scheds.append(sched)
+        starts.append(start)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+        with torch.cuda.stream(streams[t]):
+            for e in ev:
+                e.record()
+        evs.append(ev)
+    torch.cuda.synchronize()
+    barrier()
+    cur = torch.cuda.current_stream(dev)
+    errors = []
+    go = threading.Barrier(T)
+
+    def issue(t):
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(streams[t]):
+                streams[t].wait_stream(cur)
+                go.wait()                                             # the threads start issuing together
+                scheds[t].run(0, starts[t])
+                scheds[t].run(starts[t], starts[t] + R * Kt, events=evs[t], every=Kt)
+                scheds[t].run()
+        except Exception as e:                                        # noqa: BLE001 — re-raised on the main thread
+            errors.append(e)
+    t_start = time.perf_counter()
+    threads = [threading.Thread(target=issue, args=(t,)) for t in range(T)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for st in streams:
+        cur.wait_stream(st)
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    if errors:
+        raise errors[0]
+    barrier()
+    ms = [max(evs[t][r].elapsed_time(evs[t][r + 1]) for t in range(T)) for r in range(R)]
+    # cross-check: all timed launches over the device time from the first stream's first event to the last stream's
+    # last one (longer than R regions by the stagger) — must agree with the per-region figure
+    span = max(evs[a][0].elapsed_time(evs[b][R]) for a in range(T) for b in range(T))
+    time_step_regions_mt.last_span_ms_per_step = span / (R * K)
+    issue_desc = ("g2048_step_list_timed via StepSchedule from %d host threads on %d streams (thread t issues env sets t, t+%d, "
+                  "...; a region is %d launches per stream; one kernel launch per env step); %s"
+                  % (T, T, T, Kt, "chained launches (G2048_FLAG_CHAINED | G2048_FLAG_CHAIN_INTERLEAVED)" if chained else "plain launches"))
+    return max_over_ranks_vec(ms), issue_desc, t_start, t_end
 
 
 def run_ours(args):
@@ -418,8 +516,17 @@ def run_ours(args):
     if sampler:
         sampler.wait_first_sample()            # BEFORE the spin-up: nothing sleeps between warm-up and the clock
     t_spin = time.perf_counter()
-    region_ms, issue, t_start, t_end = time_step_regions(torch, g, games, pool, args.spinup, W, K, R, small, barrier,
-                                                         max_over_ranks_vec)
+    chained = "interleaved" if args.chain == "on" else False
+    T = args.issue_threads
+    if T == 0:                       # auto: a second issuing thread once the GPU outruns one (~2.4 us per launch)
+        T = 2 if (small and S % 2 == 0 and K % 2 == 0) else 1
+
+    def regions(gm, pl, spin, Kx, Rx, small_x, ch):
+        if T > 1 and small_x:
+            return time_step_regions_mt(torch, g, gm, pl, spin, W, Kx, Rx, T, barrier, max_over_ranks_vec, ch)
+        return time_step_regions(torch, g, gm, pl, spin, W, Kx, Rx, small_x, barrier, max_over_ranks_vec, ch)
+    region_ms, issue, t_start, t_end = regions(games, pool, args.spinup, K, R, small, chained)
+    time_step_regions_mt.headline_span = getattr(time_step_regions_mt, "last_span_ms_per_step", None) if (T > 1 and small) else None
     clocks = sampler.stop(t_spin, t_end) if sampler else None
     if clocks is not None:
         clocks["window"] = "spin-up + warm-up + timed regions (contiguous step launches)"
@@ -427,6 +534,22 @@ def run_ours(args):
     value = total_envs * K / (ms * 1e-3)
     launch_s = ms * 1e-3 / K              # a region holds only step-kernel launches, back to back
     checksum = state_checksum(torch, dist, games, total_envs, rank, n, world, dev)
+    # One long region (two events around `--long-region` launches): an event between two launches is a full drain and
+    # ramp of the launch pipeline — every region of K launches pays one, ~5 % of a region at the driver's K = 20.
+    long_region = None
+    if args.long_region > 0:
+        Lr = args.long_region - args.long_region % T
+        l_ms, _, _, _ = regions(games, pool, 256, Lr, 1, small, chained)
+        long_region = {"launches": Lr, "ms_per_step": l_ms[0] / Lr, "value": total_envs * Lr / (l_ms[0] * 1e-3), "unit": UNIT,
+                       "roofline_frac": ALG_BYTES_PER_STEP * n / (l_ms[0] * 1e-3 / Lr) / 1e9 / hbm_peak()[0]}
+    # the same launches without the chain (every launch waits for the whole previous grid): what round 2's first
+    # half measured; continues the same env sets, after the checksum
+    plain = None
+    if chained and not args.no_plain:
+        p_ms, p_issue, _, _ = regions(games, pool, max(args.spinup // 8, 256), K, max(R // 2, 5), small, False)
+        pm = statistics.median(p_ms)
+        plain = {"value": total_envs * K / (pm * 1e-3), "unit": UNIT, "ms_per_step": pm / K, "repeats": len(p_ms),
+                 "roofline_frac": ALG_BYTES_PER_STEP * n / (pm * 1e-3 / K) / 1e9 / hbm_peak()[0], "issue": p_issue}
 
     # ---- weak-scaling extra at N > 1 (args.envs boards PER GPU): what round 1's SCALE file measured ---------
     weak = None
@@ -436,7 +559,7 @@ def run_ours(args):
         nw = args.envs
         wg, wp = make_workload(nw, nw * world)
         w_ms, w_issue, _, _ = time_step_regions(torch, g, wg, wp, max(args.spinup // 8, 256), W, K, max(R // 2, 5),
-                                                nw < args.small_below, barrier, max_over_ranks_vec)
+                                                nw < args.small_below, barrier, max_over_ranks_vec, chained)
         wm = statistics.median(w_ms)
         weak = {"scaling": "weak", "envs_per_gpu": nw, "global_envs": nw * world, "value": nw * world * K / (wm * 1e-3),
                 "unit": UNIT, "ms_per_step": wm / K, "repeats": len(w_ms),
@@ -487,20 +610,17 @@ def run_ours(args):
         for gm in g4:
             gm.reset()
             gm.step_many(policy="legal", n_steps=200)               # play into the mid-game (mean ~5 empty cells)
-        acts4 = [torch.empty(n4, dtype=torch.uint8, device=dev) for _ in range(S4)]
+        # (the kernel WRITES the actions it draws: one row per env set — set s always gets row s, S4 rows in the pool)
+        acts4 = torch.empty((S4, n4), dtype=torch.uint8, device=dev)
         K4, R4, spin4 = 50, 25, 4096
-        sched = g.StepSchedule()
-        for j in range(spin4 + R4 * K4):
-            sched.add(g4[j % S4], acts4[j % S4], policy="legal")
-        sched.build()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(R4 + 1)]
-        for e in ev:
-            e.record()
-        torch.cuda.synchronize()
-        sched.run(0, spin4)
-        sched.run(spin4, spin4 + R4 * K4, events=ev, every=K4)
-        torch.cuda.synchronize()
-        m4 = statistics.median(ev[r].elapsed_time(ev[r + 1]) for r in range(R4)) / K4          # ms per step
+        T4 = T if (S4 % T == 0 and K4 % T == 0) else 1
+        if T4 > 1:
+            r4, issue4, _, _ = time_step_regions_mt(torch, g, g4, acts4, spin4, 0, K4, R4, T4, barrier, max_over_ranks_vec,
+                                                    chained, policy="legal")
+        else:
+            r4, issue4, _, _ = time_step_regions(torch, g, g4, acts4, spin4, 0, K4, R4, True, barrier, max_over_ranks_vec,
+                                                 chained, policy="legal")
+        m4 = statistics.median(r4) / K4                                                      # ms per step
         empties = float((g4[0].boards == 0).sum(dim=1).float().mean())
         bytes4 = 40                                   # board in 16 + mask in 1 + board out 16 + mask out 1 + action 1 + reward 4 + done 1
         peak4 = hbm_peak()[0]
@@ -509,8 +629,8 @@ def run_ours(args):
                    "value": n4 / (m4 * 1e-3), "unit": UNIT, "us_per_step": m4 * 1e3, "launches_per_step": 1,
                    "kernel": "g2048_step_kernel<O_MASK, false, POLICY_LEGAL>", "algorithmic_bytes_per_step": bytes4,
                    "roofline_frac": bytes4 * n4 / (m4 * 1e-3) / 1e9 / peak4, "mean_empty_cells": empties,
-                   "issue": "g2048_step_list_timed via StepSchedule", "steps": K4, "repeats": R4}
-        del g4, acts4, sched
+                   "issue": issue4, "steps": K4, "repeats": R4}
+        del g4, acts4
         torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through the C-ABI handle, copies inside the timed region ----------
@@ -560,6 +680,7 @@ def run_ours(args):
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
         "timing": {"issue": issue, "statistic": "median over `repeats` back-to-back regions of `steps` launches (CUDA events on the "
                                 "launching stream, max over ranks per region)",
+                   "issue_threads": T, "ms_per_step_all_regions_span": getattr(time_step_regions_mt, "headline_span", None),
                    "spinup_launches": args.spinup, "ms_per_step_min": min(region_ms) / K,
                    "ms_per_step_max": max(region_ms) / K, "ms_per_step_mean": statistics.fmean(region_ms) / K},
         "state_checksum": checksum,
@@ -574,6 +695,8 @@ def run_ours(args):
                 "api": "g2048_env_step_host (pinned host buffers)", "checksum": chk},
         "e2e_compact": e2e_compact,
         "weak": weak,
+        "plain_launches": plain,
+        "long_region": long_region,
         "fused": fused,
         "config4": config4,
         "gpu_launches": K * R, "e2e_gpu_launches": e2e_launches,
@@ -616,10 +739,10 @@ def main():
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling extra block at N > 1")
     ap.add_argument("--sets", type=int, default=32)
-    ap.add_argument("--small-below", type=int, default=1 << 20,
+    ap.add_argument("--small-below", type=int, default=1 << 21,
                     help="shards smaller than this are issued through g2048_step_list (K launches per C call): a "
-                         "Python loop issues a launch every ~6 us, a B200 steps 524,288 boards in ~6.5 us and "
-                         "131,072 in ~3 us (profiles/r02_launch_rate.log)")
+                         "Python loop issues a launch every ~6 us, a B200 steps 524,288 boards in ~4.7 us and "
+                         "131,072 in ~1.3 us (profiles/r02_launch_rate.log); 0 forces the Python loop")
     ap.add_argument("--action-pool", type=int, default=16)
     ap.add_argument("--fused-steps", type=int, default=32, help="steps per g2048_step_many launch (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=200)
@@ -627,6 +750,15 @@ def main():
     ap.add_argument("--ref-steps-per-proc", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 extra block (N = 1)")
+    ap.add_argument("--chain", choices=["on", "off"], default="on",
+                    help="on: the step launches are chained launches (include/g2048.h, G2048_FLAG_CHAINED): each depends "
+                         "on the previous step of its own env set warp by warp; off: plain launches")
+    ap.add_argument("--issue-threads", type=int, default=0,
+                    help="host threads (and streams) that issue the step launches through g2048_step_list, each its own "
+                         "env sets; 0 = auto (2 when --sets and --steps are even: one thread issues a launch every ~2.4 us, "
+                         "two ~1.4 us between them, a B200 steps 131,072 boards in ~1.3 us; profiles/r02_issue_threads.log)")
+    ap.add_argument("--long-region", type=int, default=4000, help="launches of the single long timed region (extra block; 0 = skip)")
+    ap.add_argument("--no-plain", action="store_true", help="skip the plain-launch extra block (the headline's launches unchained)")
     args = ap.parse_args()
     guard_stdout()
     if args.impl == "reference":

@@ -202,29 +202,28 @@ class BatchedGame2048:
 
     def _chain_args(self, a, chained):
         """Chained launches (G2048StepArgs.chain / G2048_FLAG_CHAINED) for the step call `a`; chained = False, True or
-        "interleaved" (see step()).  The env's chain buffer is made (zeroed) at the first chained step; from then on
-        EVERY step launch of this env carries it, chained or not — the kernel publishes the finished warps of every
-        launch, so the next one may chain to it.  A step that follows anything else this class did to the env's
-        state (reset, set_boards, step_many, ...), or that changes between direct and interleaved chaining (another
-        launch shape), is issued unchained whatever the caller promised."""
+        "interleaved" (see step()).  The env's chain buffer is made (zeroed) at the first chained step.  A chained step
+        that follows anything else this class did to the env's state (reset, set_boards, step_many, a plain step,
+        ...), or that changes between direct and interleaved chaining (another launch shape), carries the buffer but
+        not the flag: it waits for all earlier work like any launch and publishes, so the NEXT step can chain to it.
+        Plain steps are launched without the buffer, in the full-machine shape."""
         if chained not in (False, True, "interleaved"):
             raise ValueError("chained must be False, True or 'interleaved'")
-        if chained and self._chain is None:
-            if self._step_counter is not None:
+        if not chained or self._step_counter is not None:
+            if chained:
                 raise G2048Error("chained steps are not available with a device-side step counter")
+            # a plain launch: the full-machine shape, outside the protocol — the next chained step starts a new chain
+            a.chain = None
+            self._chain_broken = True
+            return
+        if self._chain is None:
             self._chain = torch.zeros(_lib.CHAIN_WORDS, dtype=torch.int64, device=self.device)
             self._chain_broken = True
-        if self._chain is None or self._step_counter is not None:
-            a.chain = None
-            self._chain_broken = True          # a launch outside the protocol: the next chained step starts a new chain
-            return
         a.chain = self._chain.data_ptr()
         mode = "interleaved" if chained == "interleaved" else "direct"
-        if not chained:
-            mode = self._chain_mode             # an unchained step in between keeps the chain's shape
         if mode == "interleaved":
             a.flags |= _lib.FLAG_CHAIN_INTERLEAVED
-        if chained and not self._chain_broken and mode == self._chain_mode:
+        if not self._chain_broken and mode == self._chain_mode:
             a.flags |= _lib.FLAG_CHAINED
         self._chain_broken = False
         self._chain_mode = mode

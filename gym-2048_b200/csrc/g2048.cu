@@ -191,7 +191,7 @@ constexpr uint32_t kFlagChained = 0x20000000u;       // internal: G2048_FLAG_CHA
 #define G2048_CHAIN_NARROW_CTAS_PER_SM 1  // launches share the machine side by side, each one CTA per SM
 #endif
 constexpr unsigned kChainThreads = G2048_CHAIN_THREADS, kChainCtasPerSm = G2048_CHAIN_CTAS_PER_SM,
-                   kChainNarrowCtasPerSm = G2048_CHAIN_NARROW_CTAS_PER_SM;
+                   kChainNarrowCtasPerSm = G2048_CHAIN_NARROW_CTAS_PER_SM, kChainNarrowMaxIters = 16u;
 // (a call whose env ids cross a multiple of 2^32 is two launches: the second one uses the upper half of the buffer)
 constexpr unsigned kChainLaunchWords = G2048_CHAIN_WORDS / 2u;
 constexpr unsigned kChainSlices = kChainLaunchWords / (kChainThreads / 32u);     // CTAs a launch has words for
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     __syncthreads();                        // every thread of the CTA has read the index before thread 0 can arrive
   }
 #if !G2048_TMA
-  if (i >= n && !chain) return;             // (a chained warp stays whole: it publishes after its last store)
+  if (i >= n && p.chain == nullptr) return; // (a chained warp stays whole: it publishes after its last store)
 #endif
   // Grid-stride loop, software-pipelined one board ahead.  orient() consumes the loaded board
   // right away, so the next board is prefetched into the same registers (no rotation copies)
@@ -699,19 +699,20 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kerne
     i = i_next;
   }
   }
-  if (chain) {
+  if (p.chain != nullptr) {                  // (everything is re-derived from the parameters here: nothing of the chain
     // Publish: the warp's stores are ordered before lane 0's release store by the warp barrier, and the release
-    // makes them visible at GPU scope before the word.
+    // makes them visible at GPU scope before the word.                         stays in registers through the loop)
     __syncwarp();
     if ((threadIdx.x & 31u) == 0u)
-      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(const_cast<unsigned long long*>(chain_word)), "l"(p.chain_tag) : "memory");
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.chain + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))),
+                   "l"(p.chain_tag) : "memory");
 #if G2048_PDL && !G2048_NOWAIT && !G2048_CHAIN_NO_LATE_WAIT
     // A chained launch did not wait for the previous grid before its work — it waits for it now, before it ENDS.
     // Stream order is transitive only through kernels that wait: a kernel behind this one (a plain step of another
     // env set, any programmatic dependent launch) waits for THIS grid to complete and must be able to conclude that
     // everything issued before it has completed too.  The launch in front of us started earlier and is normally
     // done by now; the words above are already published, so no successor is held up.
-    if (chained) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.flags & kFlagChained) asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
   }
 #endif
@@ -1292,8 +1293,16 @@ static void step_launch_config(uint64_t n, int chain, cudaStream_t s, cudaLaunch
     //   interleaved chains (several env sets round-robin): one CTA per SM — consecutive launches are independent,
     //     five of them share an SM side by side and every CTA lives four times as long, which amortises its start
     //     and its end (1 Mi boards 10.8 -> 9.05 us, 262,144 4.4 -> 2.5 us; profiles/r02_chain_shapes.log).
+    //     A launch that alone would run more than kChainNarrowMaxIters boards per thread gets two CTAs per SM: it
+    //     costs 2 % in steady state (1 Mi boards: 9.23 vs 9.03 us) but its drain at a synchronisation point — an
+    //     event every 20 launches in the driver's benchmark — is half as long (9.78 vs 10.50 us per step there;
+    //     profiles/r02_chain_bench_shapes.log).  The shape depends on n and the flag only: it is the chain's.
     const uint64_t need = (n + kChainThreads - 1) / kChainThreads;
-    uint64_t cap = (uint64_t)sm_count() * (chain == 2 ? kChainNarrowCtasPerSm : kChainCtasPerSm);
+    uint64_t per_sm = kChainCtasPerSm;
+    if (chain == 2)
+      per_sm = n > (uint64_t)sm_count() * kChainThreads * kChainNarrowCtasPerSm * kChainNarrowMaxIters ? 2u * kChainNarrowCtasPerSm
+                                                                                                    : kChainNarrowCtasPerSm;
+    uint64_t cap = (uint64_t)sm_count() * per_sm;
     if (cap > kChainSlices) cap = kChainSlices;
     cfg.gridDim = dim3((unsigned)(need < cap ? need : cap));
     cfg.blockDim = dim3(kChainThreads);

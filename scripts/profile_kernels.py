@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Launch one step-kernel specialisation repeatedly, for ncu:  python scripts/profile_kernels.py <lean|mask|all|eprun|eval> [n] [launches]
+"""Launch one step-kernel specialisation repeatedly, for ncu:  python scripts/profile_kernels.py <lean|chain|chain_direct|mask|all|eprun|eval> [n] [launches]
 (8 env sets stepped round-robin so the working set exceeds the L2 at 1 Mi boards.)"""
 import os
 import sys
@@ -9,7 +9,7 @@ import torch  # noqa: E402
 
 import gym_2048_b200 as g  # noqa: E402
 
-SETS = {"lean": (), "mask": ("legal_mask",), "all": g.ALL_OUTPUTS, "eprun": None, "eval": ("illegal", "highest", "legal_mask")}
+SETS = {"lean": (), "chain": (), "chain_direct": (), "mask": ("legal_mask",), "all": g.ALL_OUTPUTS, "eprun": None, "eval": ("illegal", "highest", "legal_mask")}
 
 
 def main():
@@ -32,6 +32,15 @@ def main():
     if which == "mask":                                   # config 4: mid-game boards under the random-legal policy
         for gm in games:
             gm.step_many(policy="legal", n_steps=200)
+    if which.startswith("chain"):                         # the benchmark's launches: chained, issued by one C call
+        if which == "chain_direct":
+            games = games[:1]
+        sched = g.StepSchedule()
+        for j in range(launches):
+            sched.add(games[j % len(games)], pool[j % 8], chained="interleaved" if which == "chain" else True)
+        sched.run()
+        torch.cuda.synchronize()
+        return
     for j in range(launches):
         games[j % 8].step(pool[j % 8])
     torch.cuda.synchronize()

@@ -357,7 +357,8 @@ def test_bench_prints_one_contract_line_on_a_small_workload():
         assert k in d, k
     assert d["metric"] == "env_steps_per_sec" and d["scaling"] == "strong" and d["dtype"] == "u8" and d["value"] > 1e9
     assert d["config"]["global_envs"] == 65536 and d["gpu_launches"] == 12 and d["repeats"] == 3
-    assert "g2048_step_list" in d["timing"]["issue"]
+    assert "g2048_step_list" in d["timing"]["issue"] and "chained launches" in d["timing"]["issue"]
+    assert d["timing"]["issue_threads"] == 2 and d["plain_launches"]["value"] > 1e9 and d["long_region"]["launches"] == 4000
     r = d["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic_kind"]
     assert abs(r["achieved"] - 38 * 65536 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
@@ -366,3 +367,7 @@ def test_bench_prints_one_contract_line_on_a_small_workload():
     # the Python-loop issue path (forced) steps the same boards: identical checksum
     d2 = run("--small-below", "0")
     assert "Python loop" in d2["timing"]["issue"] and d2["state_checksum"] == d["state_checksum"]
+    # plain launches from one issuing thread (the first half of round 2): the same boards again
+    d3 = run("--chain", "off", "--issue-threads", "1")
+    assert "plain launches" in d3["timing"]["issue"] and d3["plain_launches"] is None
+    assert d3["state_checksum"] == d["state_checksum"]
