@@ -100,6 +100,29 @@ def test_interleaved_chains_round_robin_schedule():
         _same_state(a, b)
 
 
+def test_schedule_issued_by_two_host_threads_on_two_streams():
+    """StepSchedule.run_threads: the games dealt to two issuing threads / streams, chained launches — the same boards
+    as the same steps made one by one."""
+    import torch
+    import gym_2048_b200 as g
+    n, K, S = 131072, 400, 4
+    mk = lambda s: g.BatchedGame2048(n, seed=13, env_id_base=s * n, outputs=("episode",) if s % 2 else ())   # noqa: E731
+    A, B = [mk(s) for s in range(S)], [mk(s) for s in range(S)]
+    for x in A + B:
+        x.reset()
+    acts = _acts(16, n, seed=3)
+    sched = g.StepSchedule()
+    for j in range(K):
+        sched.add(A[j % S], acts[j % 16], chained="interleaved")
+    sched.run(0, 40)                      # a first slice from the calling thread, the rest from two threads
+    sched.run_threads(2)
+    for j in range(K):
+        B[j % S].step(acts[j % 16])
+    torch.cuda.synchronize()
+    for a, b in zip(A, B):
+        _same_state(a, b)
+
+
 def test_chained_and_plain_env_sets_share_a_stream():
     """A chained launch does not wait for the previous grid before its work; stream order must still hold for what
     follows it: a PLAIN env stepped in between (programmatic dependent launches that wait for "the previous grid")
