@@ -13,8 +13,8 @@ own env set warp by warp instead of on the whole previous grid; `--chain off` fo
 the `plain_launches` block times anyway) issued through g2048_step_list by `--issue-threads` host
 threads (auto: two, each with its own stream and env sets).  Prints ONE JSON line with `value`
 (device-resident throughput), `e2e` (host-buffer C-ABI call, copies inside the timed
-region), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, `long_region` (one region of
-`--long-region` launches: no event in between), and `fused`: the same workload through
+region), `roofline`, `cpu_baseline`, `clocks`, `gpu_launches`, `long_region` (regions of
+`--long-region` launches: an event every 1000 launches instead of every K), and `fused`: the same workload through
 g2048_step_many (`--fused-steps` steps per launch, boards in registers in between) — an extra, not the
 headline.
 
@@ -466,6 +466,16 @@ def run_ours(args):
         args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1 and args.pin_cores and hasattr(os, "sched_setaffinity"):
+        # N processes x (main + 2 issuing threads + NCCL proxy) on one box: give every rank its own cores, so that no
+        # rank's issuing threads wait for a core another rank is spinning on (max over ranks is what is reported)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 3:
+                os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+        except OSError:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner off stdout: ONE JSON line
@@ -534,19 +544,21 @@ def run_ours(args):
     value = total_envs * K / (ms * 1e-3)
     launch_s = ms * 1e-3 / K              # a region holds only step-kernel launches, back to back
     checksum = state_checksum(torch, dist, games, total_envs, rank, n, world, dev)
-    # One long region (two events around `--long-region` launches): an event between two launches is a full drain and
-    # ramp of the launch pipeline — every region of K launches pays one, ~5 % of a region at the driver's K = 20.
+    # Long regions (`--long-region` launches between two events, median of 5): an event between two launches is a full
+    # drain and ramp of the launch pipeline — every region of K launches pays one, ~5 % of a region at the driver's K = 20.
     long_region = None
     if args.long_region > 0:
         Lr = args.long_region - args.long_region % T
-        l_ms, _, _, _ = regions(games, pool, 256, Lr, 1, small, chained)
-        long_region = {"launches": Lr, "ms_per_step": l_ms[0] / Lr, "value": total_envs * Lr / (l_ms[0] * 1e-3), "unit": UNIT,
-                       "roofline_frac": ALG_BYTES_PER_STEP * n / (l_ms[0] * 1e-3 / Lr) / 1e9 / hbm_peak()[0]}
+        l_ms, _, _, _ = regions(games, pool, max(args.spinup // 2, 256), Lr, 5, small, chained)   # (the clocks ramp again after the checksum's idle gap)
+        lm = statistics.median(l_ms)
+        long_region = {"launches": Lr, "repeats": len(l_ms), "ms_per_step": lm / Lr, "ms_per_step_max": max(l_ms) / Lr,
+                       "value": total_envs * Lr / (lm * 1e-3), "unit": UNIT,
+                       "roofline_frac": ALG_BYTES_PER_STEP * n / (lm * 1e-3 / Lr) / 1e9 / hbm_peak()[0]}
     # the same launches without the chain (every launch waits for the whole previous grid): what round 2's first
     # half measured; continues the same env sets, after the checksum
     plain = None
     if chained and not args.no_plain:
-        p_ms, p_issue, _, _ = regions(games, pool, max(args.spinup // 8, 256), K, max(R // 2, 5), small, False)
+        p_ms, p_issue, _, _ = regions(games, pool, max(args.spinup // 2, 256), K, max(R // 2, 5), small, False)
         pm = statistics.median(p_ms)
         plain = {"value": total_envs * K / (pm * 1e-3), "unit": UNIT, "ms_per_step": pm / K, "repeats": len(p_ms),
                  "roofline_frac": ALG_BYTES_PER_STEP * n / (pm * 1e-3 / K) / 1e9 / hbm_peak()[0], "issue": p_issue}
@@ -558,8 +570,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         nw = args.envs
         wg, wp = make_workload(nw, nw * world)
-        w_ms, w_issue, _, _ = time_step_regions(torch, g, wg, wp, max(args.spinup // 8, 256), W, K, max(R // 2, 5),
-                                                nw < args.small_below, barrier, max_over_ranks_vec, chained)
+        w_ms, w_issue, _, _ = regions(wg, wp, max(args.spinup // 2, 256), K, max(R // 2, 5), nw < args.small_below, chained)
         wm = statistics.median(w_ms)
         weak = {"scaling": "weak", "envs_per_gpu": nw, "global_envs": nw * world, "value": nw * world * K / (wm * 1e-3),
                 "unit": UNIT, "ms_per_step": wm / K, "repeats": len(w_ms),
@@ -757,7 +768,9 @@ def main():
                     help="host threads (and streams) that issue the step launches through g2048_step_list, each its own "
                          "env sets; 0 = auto (2 when --sets and --steps are even: one thread issues a launch every ~2.4 us, "
                          "two ~1.4 us between them, a B200 steps 131,072 boards in ~1.3 us; profiles/r02_issue_threads.log)")
-    ap.add_argument("--long-region", type=int, default=4000, help="launches of the single long timed region (extra block; 0 = skip)")
+    ap.add_argument("--pin-cores", type=int, default=1,
+                    help="N > 1: restrict every rank to its own 1/N of the host cores (1) or leave placement to the OS (0)")
+    ap.add_argument("--long-region", type=int, default=1000, help="launches of a long timed region (extra block, median of 5; 0 = skip)")
     ap.add_argument("--no-plain", action="store_true", help="skip the plain-launch extra block (the headline's launches unchained)")
     args = ap.parse_args()
     guard_stdout()

@@ -358,7 +358,7 @@ def test_bench_prints_one_contract_line_on_a_small_workload():
     assert d["metric"] == "env_steps_per_sec" and d["scaling"] == "strong" and d["dtype"] == "u8" and d["value"] > 1e9
     assert d["config"]["global_envs"] == 65536 and d["gpu_launches"] == 12 and d["repeats"] == 3
     assert "g2048_step_list" in d["timing"]["issue"] and "chained launches" in d["timing"]["issue"]
-    assert d["timing"]["issue_threads"] == 2 and d["plain_launches"]["value"] > 1e9 and d["long_region"]["launches"] == 4000
+    assert d["timing"]["issue_threads"] == 2 and d["plain_launches"]["value"] > 1e9 and d["long_region"]["launches"] == 1000
     r = d["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic_kind"]
     assert abs(r["achieved"] - 38 * 65536 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
