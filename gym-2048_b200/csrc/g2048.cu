@@ -89,6 +89,14 @@ constexpr int kCtasPerSm = G2048_CTAS_PER_SM;
 #define G2048_STEP_CTAS_PER_SM (G2048_TMA ? 2 : 1)
 #endif
 constexpr int kStepThreads = G2048_STEP_THREADS, kStepCtasPerSm = G2048_STEP_CTAS_PER_SM;
+#ifndef G2048_STEP_MAXREG       // experiments: cap the step kernels' registers (0 = what the launch bounds allow: 64)
+#define G2048_STEP_MAXREG 0
+#endif
+#if G2048_STEP_MAXREG
+#define G2048_STEP_BOUNDS __maxnreg__(G2048_STEP_MAXREG)
+#else
+#define G2048_STEP_BOUNDS __launch_bounds__(kStepThreads, kStepCtasPerSm)
+#endif
 static_assert(kThreads == G2048_THREADS, "g2048_internal.h and g2048.cu disagree on the CTA size");
 
 // The current device of the calling thread.  A launch list (g2048_step_list) issues thousands of launches on one
@@ -425,7 +433,7 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 // the legal moves p.legal_mask holds for the board (the mask the previous step wrote) — and writes it to
 // p.actions_out: BASELINE config 4's "sample a legal action, step, return the new mask" is ONE launch.
 template <uint32_t OUT, bool COUNTER, int POLICY = 0>
-__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_kernel(const StepParams p) {
+__global__ void G2048_STEP_BOUNDS g2048_step_kernel(const StepParams p) {
   static_assert(POLICY == 0 || (!G2048_TMA && !G2048_PIPELINE), "the policy kernels exist for the plain loop only");
   static_assert(POLICY != 2 || (OUT & (O_MASK | O_GENERIC)) != 0u, "the random-legal policy reads and writes the legal mask");
 #if G2048_LUT_GLOBAL
@@ -761,7 +769,7 @@ struct ManyParams {
 // itself — the action of step k is drawn from the policy-tag stream at index step_index + k, for the legal policy
 // among the legal moves of the board the previous step handed back — so a whole random rollout is one launch.
 template <bool EXTRAS, int POLICY>
-__global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) g2048_step_many_kernel(const ManyParams p) {
+__global__ void G2048_STEP_BOUNDS g2048_step_many_kernel(const ManyParams p) {
   __shared__ alignas(128) Board4 s_lut[1024];
   __shared__ alignas(8) uint64_t s_lut_bar;
   __shared__ Sel4 s_sel[8];
