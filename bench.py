@@ -454,6 +454,30 @@ def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max
     return max_over_ranks_vec(ms), issue_desc, t_start, t_end
 
 
+def rank_cpus(allowed, local, world):
+    """The logical CPUs of rank `local`: whole physical cores (hyper-thread siblings stay together, so that no rank's
+    issuing thread shares a core with another rank's), dealt out in contiguous runs of cores."""
+    groups, seen = [], set()
+    for c in allowed:
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    sib.update(range(int(lo), int(hi or lo) + 1))
+        except (OSError, ValueError):
+            pass
+        sib = sorted(x for x in sib if x in allowed)
+        seen.update(sib)
+        groups.append(sib)
+    per = len(groups) // world
+    if per < 1:
+        return []
+    return [c for grp in groups[local * per:(local + 1) * per] for c in grp]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -470,10 +494,9 @@ def run_ours(args):
         # N processes x (main + 2 issuing threads + NCCL proxy) on one box: give every rank its own cores, so that no
         # rank's issuing threads wait for a core another rank is spinning on (max over ranks is what is reported)
         try:
-            cores = sorted(os.sched_getaffinity(0))
-            per = len(cores) // world
-            if per >= 3:
-                os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+            mine = rank_cpus(sorted(os.sched_getaffinity(0)), local, world)
+            if len(mine) >= 2:
+                os.sched_setaffinity(0, mine)
         except OSError:
             pass
     if world > 1:

@@ -165,3 +165,17 @@ def test_argument_checks_that_need_no_gpu():
     assert L.g2048_step_many(C.byref(m), None) == -1 and b"unknown flags" in L.g2048_last_error()
     m.n_steps = 0                       # nothing to do is not an error
     assert L.g2048_step_many(C.byref(m), None) == 0
+
+
+def test_bench_rank_cpus_are_disjoint_whole_cores():
+    """bench.py pins every rank of an N-GPU run to its own physical cores: the sets are disjoint and lie in the allowed set."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    allowed = sorted(os.sched_getaffinity(0))
+    for world in (1, 2, 4, 8):
+        sets = [bench.rank_cpus(allowed, r, world) for r in range(world)]
+        flat = [c for s_ in sets for c in s_]
+        assert len(flat) == len(set(flat)) and set(flat) <= set(allowed)
+        assert world > len(allowed) or all(sets)
