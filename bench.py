@@ -374,6 +374,9 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
     return max_over_ranks_vec(ms), issue, t_start, t_end
 
 
+SPAN = {"ms_per_step": None}      # time_step_regions_mt's cross-check of its last call (see there)
+
+
 def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max_over_ranks_vec, chained="interleaved",
                          policy=None):
     """The same launches as time_step_regions — global launch j steps env set j % S with action row j % P — issued by T
@@ -447,7 +450,7 @@ def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max
     # cross-check: all timed launches over the device time from the first stream's first event to the last stream's
     # last one (longer than R regions by the stagger) — must agree with the per-region figure
     span = max(evs[a][0].elapsed_time(evs[b][R]) for a in range(T) for b in range(T))
-    time_step_regions_mt.last_span_ms_per_step = span / (R * K)
+    SPAN["ms_per_step"] = span / (R * K)
     issue_desc = ("g2048_step_list_timed via StepSchedule from %d host threads on %d streams (thread t issues env sets t, t+%d, "
                   "...; a region is %d launches per stream; one kernel launch per env step); %s"
                   % (T, T, T, Kt, "chained launches (G2048_FLAG_CHAINED | G2048_FLAG_CHAIN_INTERLEAVED)" if chained else "plain launches"))
@@ -559,7 +562,7 @@ def run_ours(args):
             return time_step_regions_mt(torch, g, gm, pl, spin, W, Kx, Rx, T, barrier, max_over_ranks_vec, ch)
         return time_step_regions(torch, g, gm, pl, spin, W, Kx, Rx, small_x, barrier, max_over_ranks_vec, ch)
     region_ms, issue, t_start, t_end = regions(games, pool, args.spinup, K, R, small, chained)
-    time_step_regions_mt.headline_span = getattr(time_step_regions_mt, "last_span_ms_per_step", None) if (T > 1 and small) else None
+    headline_span = SPAN["ms_per_step"] if (T > 1 and small) else None
     clocks = sampler.stop(t_spin, t_end) if sampler else None
     if clocks is not None:
         clocks["window"] = "spin-up + warm-up + timed regions (contiguous step launches)"
@@ -714,7 +717,7 @@ def run_ours(args):
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
         "timing": {"issue": issue, "statistic": "median over `repeats` back-to-back regions of `steps` launches (CUDA events on the "
                                 "launching stream, max over ranks per region)",
-                   "issue_threads": T, "ms_per_step_all_regions_span": getattr(time_step_regions_mt, "headline_span", None),
+                   "issue_threads": T, "ms_per_step_all_regions_span": headline_span,
                    "spinup_launches": args.spinup, "ms_per_step_min": min(region_ms) / K,
                    "ms_per_step_max": max(region_ms) / K, "ms_per_step_mean": statistics.fmean(region_ms) / K},
         "state_checksum": checksum,
