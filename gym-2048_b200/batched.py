@@ -243,8 +243,8 @@ class BatchedGame2048:
         in advance, the in-kernel policies, several envs stepped round-robin.  The launch then depends on its
         predecessor warp by warp instead of waiting for the whole grid to drain, with identical results.  True: this
         env is stepped back to back (1 Mi boards 10.5 -> 9.4 us per step, 262,144 4.1 -> 3.6 us); "interleaved":
-        steps of OTHER envs sit between two steps of this one (several env sets round-robin: 10.8 -> 9.05 us and
-        4.4 -> 2.5 us).  Leave it False when a policy kernel wrote `actions` after the previous step (a closed
+        steps of OTHER envs sit between two steps of this one (two or more env sets round-robin: 10.8 -> 9.05 us and
+        4.4 -> 2.5 us; with a single set this shape is slower than plain launches, profiles/r02_chain_sets.log).  Leave it False when a policy kernel wrote `actions` after the previous step (a closed
         loop), or after touching the env's tensors directly.
 
         policy = "uniform" / "legal": the kernel draws the actions itself — exactly the actions sample_actions(legal=...)

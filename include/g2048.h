@@ -99,7 +99,8 @@ extern "C" {
  *          launches of this chain follow each other directly on the stream (g2048_step_n, one env set stepped
  *          in a loop) — every launch fills the machine.  Set: launches of OTHER chains sit in between (several
  *          env sets stepped round-robin) — a launch takes a fifth of every SM and up to five consecutive launches
- *          run side by side.  A wrong choice costs time, not correctness.
+ *          run side by side (it pays from two alternating sets on, profiles/r02_chain_sets.log).  A wrong choice
+ *          costs time, not correctness.
  */
 #define G2048_FLAG_CHAINED 8u
 #define G2048_FLAG_CHAIN_INTERLEAVED 16u
