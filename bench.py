@@ -433,6 +433,7 @@ def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max
                 scheds[t].run()
         except Exception as e:                                        # noqa: BLE001 — re-raised on the main thread
             errors.append(e)
+            go.abort()                                                # the other threads must not wait for this one
     t_start = time.perf_counter()
     threads = [threading.Thread(target=issue, args=(t,)) for t in range(T)]
     for th in threads:
@@ -726,7 +727,11 @@ def run_ours(args):
                      "traffic": traffic, "traffic_source": traffic_src, "traffic_kind": traffic_kind,
                      "peak_source": peak_src, "kernel": "g2048_step_kernel<0, false>",
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n,
-                     "launch_us": launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "launch_us": launch_s * 1e6, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "launch_time_definition": "region time / launches in the region (a region holds nothing but step launches). "
+                                               "Chained launches of different env sets overlap on the GPU, so this is the rate at "
+                                               "which launches complete; one chained launch running ALONE (as under ncu, which "
+                                               "serialises launches) takes longer — profiles/r02_chain_launches_summary.md"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,
                 "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "chunks": args.e2e_chunks,
                 "api": "g2048_env_step_host (pinned host buffers)", "checksum": chk},

@@ -521,8 +521,10 @@ __global__ void G2048_STEP_BOUNDS g2048_step_kernel(const StepParams p) {
       const unsigned long long want = p.chain_tag - 1ull;      // what this warp's predecessor published
       uint32_t polls = 0u;
       while (chain_seen != want) {
-        if (++polls > 16u) __nanosleep(64);
-        if (polls > (1u << 21)) __trap();                      // > 1 s: the caller chained to a launch that never ran
+        // back off: a predecessor that is merely slow (a debugger, a sanitizer, a time-sliced GPU) must not be
+        // mistaken for one that never ran — the trap comes after more than 30 s of waiting
+        if (++polls > 16u) __nanosleep(polls > 4096u ? 4000u : 64u);
+        if (polls > (1u << 23)) __trap();                      // the caller chained to a launch that never ran
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(chain_seen) : "l"(chain_word) : "memory");
       }
     }

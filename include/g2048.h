@@ -196,6 +196,9 @@ int g2048_step(const G2048StepArgs* args, void* stream);
  * Use: open-loop action sequences stepped at the launch rate of C instead of the caller's
  * language (a 131,072-board shard is stepped in ~3 us; a Python loop issues a launch every
  * ~6 us).  g2048_step_many is the variant that also keeps the boards in registers.
+ * With args->chain set the steps are chained launches (G2048_FLAG_CHAINED above): the first step carries the
+ * caller's flags, every later one the flag as well — step t+1 reads what step t wrote and rows that were there
+ * before the call.
  */
 int g2048_step_n(const G2048StepArgs* args, uint32_t n_steps, uint64_t row_stride, void* stream);
 
