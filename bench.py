@@ -377,6 +377,27 @@ def time_step_regions(torch, g, games, pool, spinup, W, K, R, small, barrier, ma
 SPAN = {"ms_per_step": None}      # time_step_regions_mt's cross-check of its last call (see there)
 
 
+def issue_plan(total, S, P, T, spinup_w, R, Kt):
+    """Who launches what when T host threads share the single-stream schedule `launch j steps env set j % S with action
+    row j % P, j < total`: thread t owns the sets t, t+T, ... and steps them round-robin, every set exactly as often
+    and with exactly the rows the single stream would (so the boards do not depend on T).  Returns per thread
+    (items, start): items = [(set, row), ...] in issue order, start = index of the first timed launch — R regions of
+    Kt launches follow it; the starts are staggered by Kt/T launches from thread to thread (taken out of the spin-up),
+    and at least max(64, 4 Kt) launches stay behind the last region where the schedule is long enough."""
+    plan = []
+    for t in range(T):
+        mine = list(range(t, S, T))
+        count = {s_: (total - s_ + S - 1) // S if s_ < total else 0 for s_ in mine}   # launches of set s_ in the single-stream order
+        items, m = [], 0
+        while any(m < count[s_] for s_ in mine):
+            items += [(s_, (s_ + m * S) % P) for s_ in mine if m < count[s_]]
+            m += 1
+        tail = max(64, 4 * Kt)
+        start = max(0, min(spinup_w // T, len(items) - R * Kt - tail) - ((T - 1 - t) * Kt) // T)
+        plan.append((items, start))
+    return plan
+
+
 def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max_over_ranks_vec, chained="interleaved",
                          policy=None):
     """The same launches as time_step_regions — global launch j steps env set j % S with action row j % P — issued by T
@@ -392,23 +413,11 @@ def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max
     dev = games[0].device
     streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
     scheds, starts, evs = [], [], []
-    for t in range(T):
+    for t, (items, start) in enumerate(issue_plan(total, S, P, T, spinup + W, R, Kt)):
         sched = g.StepSchedule()
-        mine = list(range(t, S, T))                                   # this thread's env sets
-        count = {s_: (total - s_ + S - 1) // S for s_ in mine}        # launches of set s_ in the single-stream order
-        m = 0
-        while any(m < count[s_] for s_ in mine):
-            for s_ in mine:
-                if m < count[s_]:
-                    _add(sched, games[s_], pool[(s_ + m * S) % P], chained, policy)
-            m += 1
+        for s_, row in items:
+            _add(sched, games[s_], pool[row], chained, policy)
         sched.build()
-        # region boundaries staggered by Kt/T launches from stream to stream, taken out of the spin-up (the schedule
-        # itself — how often every set is stepped — is the single-stream one: same state checksum)
-        # (and the timed regions end `tail` launches before the schedule does: a stream that is ahead of the other
-        # keeps launching while the other one is still being timed)
-        tail = max(64, 4 * Kt)
-        start = max(0, min((spinup + W) // T, len(sched) - R * Kt - tail) - ((T - 1 - t) * Kt) // T)
         assert start + R * Kt <= len(sched)
         scheds.append(sched)
         starts.append(start)

@@ -179,3 +179,26 @@ def test_bench_rank_cpus_are_disjoint_whole_cores():
         flat = [c for s_ in sets for c in s_]
         assert len(flat) == len(set(flat)) and set(flat) <= set(allowed)
         assert world > len(allowed) or all(sets)
+
+
+def test_bench_issue_plan_is_the_single_stream_schedule_per_env_set():
+    """bench.py with T issuing threads: every env set is stepped exactly as often, with exactly the action rows, and in the
+    order the single-stream schedule (launch j -> set j % S, row j % P) steps it — the state checksum cannot depend on T."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for total, S, P, T, R, K in ((16384 + 5 + 500, 32, 16, 2, 25, 20), (2048 + 5 + 500, 32, 16, 4, 25, 20), (64 + 3 + 12, 4, 16, 2, 3, 4),
+                                 (4096 + 25 * 50, 16, 16, 2, 25, 50), (300, 6, 5, 3, 2, 6)):
+        single = {}
+        for j in range(total):
+            single.setdefault(j % S, []).append(j % P)
+        plan = bench.issue_plan(total, S, P, T, total - R * K, R, K // T)
+        got = {}
+        for t, (items, start) in enumerate(plan):
+            assert all(s_ % T == t for s_, _ in items)
+            assert 0 <= start and start + R * (K // T) <= len(items)
+            for s_, row in items:
+                got.setdefault(s_, []).append(row)
+        assert got == single
+        assert sum(len(items) for items, _ in plan) == total
