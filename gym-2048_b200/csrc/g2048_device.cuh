@@ -74,6 +74,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // strength-reduced back to IADD3), shr() a right shift done as IMAD.HI.
 #ifdef G2048_HOST_SIM
 inline uint32_t addf(uint32_t x, uint32_t y) { return x + y; }
+inline uint32_t addm(uint32_t x, uint32_t y) { return x + y; }
 template <int S> inline uint32_t shr(uint32_t x) { return x >> S; }
 template <int S> inline uint32_t shl(uint32_t x) { return x << S; }
 inline uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
@@ -94,6 +95,21 @@ __device__ __forceinline__ uint32_t addf(uint32_t x, uint32_t y) {
 #ifndef G2048_SHR_ALU         // 1: constant right shifts as SHF (ALU pipe) instead of IMAD.HI (FMA-heavy, quarter rate)
 #define G2048_SHR_ALU 1
 #endif
+// An add that stays IMAD (FMA-heavy pipe) whatever ptxas would choose: for the legal-move mask, whose 45 extra
+// instructions are two thirds LOP3 — with its 19 adds left to ptxas (IADD3 on either pipe) the mask kernels are 6 %
+// slower (1 Mi boards, random-legal policy: 14.7 vs 13.8 us chained, 16.3 vs 15.4 us plain; profiles/r02_variants.log).
+#ifndef G2048_MASK_ADD_FMA
+#define G2048_MASK_ADD_FMA 1
+#endif
+__device__ __forceinline__ uint32_t addm(uint32_t x, uint32_t y) {
+#if G2048_MASK_ADD_FMA
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(kOne), "r"(y));
+  return d;
+#else
+  return x + y;
+#endif
+}
 template <int S> __device__ __forceinline__ uint32_t shr(uint32_t x) {
   return G2048_SHR_ALU ? (x >> S) : __umulhi(x, 1u << (32 - S));
 }
@@ -541,17 +557,17 @@ G2048_DEV bool full_board_is_dead(uint32_t r0, uint32_t r1, uint32_t r2, uint32_
 // A line moves toward its head iff some cell is empty with a tile right behind it, or
 // two adjacent tiles are equal.
 G2048_DEV uint32_t legal_mask(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-  // (the adds go to the FMA pipe, addf: the ALU pipe is the step kernel's critical one)
-  const uint32_t n0 = addf(r0, L7), n1 = addf(r1, L7), n2 = addf(r2, L7), n3 = addf(r3, L7);   // bit7: non-empty
+  // (the adds are pinned to the FMA pipe, addm: the ALU pipe is the step kernel's critical one)
+  const uint32_t n0 = addm(r0, L7), n1 = addm(r1, L7), n2 = addm(r2, L7), n3 = addm(r3, L7);   // bit7: non-empty
   // vertical pairs (upper u, lower l)
-  const uint32_t eqv = (~addf(r0 ^ r1, L7) & n0) | (~addf(r1 ^ r2, L7) & n1) | (~addf(r2 ^ r3, L7) & n2);
+  const uint32_t eqv = (~addm(r0 ^ r1, L7) & n0) | (~addm(r1 ^ r2, L7) & n1) | (~addm(r2 ^ r3, L7) & n2);
   const uint32_t up = (~n0 & n1) | (~n1 & n2) | (~n2 & n3) | eqv;     // hole above a tile
   const uint32_t dn = (n0 & ~n1) | (n1 & ~n2) | (n2 & ~n3) | eqv;     // hole below a tile
   // horizontal pairs: byte j of s_i is cell (i, j+1); only byte lanes 0..2 are pairs
   const uint32_t s0 = shr<8>(r0), s1 = shr<8>(r1), s2 = shr<8>(r2), s3 = shr<8>(r3);
-  const uint32_t m0 = addf(s0, L7), m1 = addf(s1, L7), m2 = addf(s2, L7), m3 = addf(s3, L7);
-  const uint32_t eqh = (~addf(r0 ^ s0, L7) & n0) | (~addf(r1 ^ s1, L7) & n1) |
-                       (~addf(r2 ^ s2, L7) & n2) | (~addf(r3 ^ s3, L7) & n3);
+  const uint32_t m0 = addm(s0, L7), m1 = addm(s1, L7), m2 = addm(s2, L7), m3 = addm(s3, L7);
+  const uint32_t eqh = (~addm(r0 ^ s0, L7) & n0) | (~addm(r1 ^ s1, L7) & n1) |
+                       (~addm(r2 ^ s2, L7) & n2) | (~addm(r3 ^ s3, L7) & n3);
   const uint32_t lf = (~n0 & m0) | (~n1 & m1) | (~n2 & m2) | (~n3 & m3) | eqh;   // hole left of a tile
   const uint32_t rt = (n0 & ~m0) | (n1 & ~m1) | (n2 & ~m2) | (n3 & ~m3) | eqh;   // hole right of a tile
   constexpr uint32_t HP = 0x00808080u;                                           // pair lanes only
