@@ -6,9 +6,11 @@
 // HBM- and issue-bound, no tensor cores.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "../../include/g2048.h"
@@ -170,15 +172,20 @@ static LaunchShape shape_for(uint64_t n, size_t static_smem, bool single_step) {
   return LaunchShape{(unsigned)ctas, block, budget > fixed ? (budget - fixed) / 1024 * 1024 : 0};
 }
 constexpr int kMaxPadSmem = 208 * 1024;
-// True the first time the calling thread asks for the current device under `seen` (one bit per device ordinal):
-// kernel attributes are per device and are set once, also for a host thread that drives several GPUs in turn.
-static bool first_use_on_current_device(uint64_t& seen) {
+// Kernel attributes are per device and are set ONCE PER PROCESS for every device (one bit per device ordinal in
+// `seen`), under a lock: a second issuing thread (StepSchedule.run_threads, bench.py --issue-threads) must neither
+// repeat the ~40 cudaFuncSetAttribute calls nor make them while the first thread is launching the same kernels
+// (legal for the runtime, but compute-sanitizer's racecheck dies on it with plain launches of padded CTAs).
+// Runs `set_attributes` the first time the current device is seen; every caller returns after they are set.
+template <typename F> static void once_per_device(std::atomic<uint64_t>& seen, std::mutex& lock, F set_attributes) {
   int dev = 0;
-  if (current_device(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  if (current_device(&dev) != cudaSuccess || dev < 0 || dev > 63) { set_attributes(); return; }
   const uint64_t bit = 1ull << dev;
-  if (seen & bit) return false;
-  seen |= bit;
-  return true;
+  if (seen.load(std::memory_order_acquire) & bit) return;
+  std::lock_guard<std::mutex> hold(lock);
+  if (seen.load(std::memory_order_relaxed) & bit) return;
+  set_attributes();
+  seen.fetch_or(bit, std::memory_order_release);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1334,8 +1341,9 @@ static void step_launch_config(uint64_t n, int chain, cudaStream_t s, cudaLaunch
 #endif
   }
   {
-    static thread_local uint64_t seen = 0;
-    if (first_use_on_current_device(seen)) {           // once per device and thread: allow the padding, prefer shared memory
+    static std::atomic<uint64_t> seen{0};
+    static std::mutex lock;
+    once_per_device(seen, lock, [] {                   // allow the padding, prefer shared memory
       for (const StepKernelEntry& e : kStepKernels) {
 #if G2048_TMA
         cudaFuncSetAttribute(e.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 50);   // a ring per CTA, two CTAs per SM
@@ -1344,7 +1352,7 @@ static void step_launch_config(uint64_t n, int chain, cudaStream_t s, cudaLaunch
         cudaFuncSetAttribute(e.fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 #endif
       }
-    }
+    });
   }
   cfg.stream = s;
 #if G2048_PDL
@@ -1547,14 +1555,15 @@ static int launch_step_many(const G2048StepManyArgs* a, uint64_t lo, uint64_t m,
   cfg.numAttrs = 1;
 #endif
   {
-    // once per device and thread: allow the padding of shape_for, prefer shared memory over L1
-    static thread_local uint64_t seen = 0;
-    if (first_use_on_current_device(seen)) {
+    // once per device: allow the padding of shape_for, prefer shared memory over L1
+    static std::atomic<uint64_t> seen{0};
+    static std::mutex lock;
+    once_per_device(seen, lock, [] {
       for (const void* k : kManyKernels) {
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPadSmem);
       }
-    }
+    });
   }
   const bool extras = a->illegal || a->boards_traj || a->legal_mask;
   const int policy = (a->flags & G2048_FLAG_POLICY_LEGAL) ? 2 : (a->flags & G2048_FLAG_POLICY_UNIFORM) ? 1 : 0;
