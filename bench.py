@@ -681,37 +681,42 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through the C-ABI handle, copies inside the timed region ----------
+    # The caller hands over pinned HOST actions and gets boards [n,16] / rewards / dones in HOST arrays, every step.
+    #   e2e            the handle's default: the boards cross PCIe 4 bits per cell and the library's host threads expand
+    #                  them into the caller's [n,16] array inside the call (G2048_BOARDS_BYTES_PACKED_WIRE)
+    #   e2e_plain_wire the same call moving the 16 bytes per board as they are (round 1 / first half of round 2)
+    #   e2e_compact    the caller ASKS for the packed boards ([n,8]; nothing is expanded)
     Ke = max(3, min(K * R, args.e2e_steps))
-    henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, n_chunks=args.e2e_chunks)
-    henv.reset()
     host_pool = torch.randint(0, 4, (8, n), dtype=torch.uint8).pin_memory()
-    for i in range(5):
-        henv.step_pinned(host_pool[i % 8])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        henv.step_pinned(host_pool[i % 8])
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    chk = float(henv.buffers.rewards.sum())        # the result is read on the host
+
+    def time_host_env(**kw):
+        henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, **kw)
+        henv.reset()
+        for i in range(5):
+            henv.step_pinned(host_pool[i % 8])
+        barrier()
+        t0 = time.perf_counter()
+        overflow = 0
+        for i in range(Ke):
+            overflow += henv.step_pinned(host_pool[i % 8]).nibble_overflow.value
+        secs = max_over_ranks(time.perf_counter() - t0)
+        chk = float(henv.buffers.rewards.sum())    # the result is read on the host
+        bsum = int(henv.buffers.boards.to(torch.int64).sum()) if kw.get("board_format") != "nibble" else None
+        launches = henv.n_chunks_effective * Ke
+        henv.close()
+        return secs, chk, bsum, overflow, launches
+    e2e_s, chk, bsum, e2e_overflow, e2e_launches = time_host_env(n_chunks=args.e2e_chunks_packed, wire="packed",
+                                                                 unpack_threads=args.unpack_threads)
     e2e_value = total_envs * Ke / e2e_s
-    e2e_launches = henv.n_chunks_effective * Ke
-    henv.close()
-    # the same call with the compact host format (boards 4 bits per cell: 13 instead of 21 bytes per board come back)
-    henv = g.HostSteppedEnv(n, seed=42, device=local, env_id_base=rank * n, n_chunks=args.e2e_chunks, board_format="nibble")
-    henv.reset()
-    for i in range(5):
-        henv.step_pinned(host_pool[i % 8])
-    barrier()
-    t0 = time.perf_counter()
-    overflow = 0
-    for i in range(Ke):
-        overflow += henv.step_pinned(host_pool[i % 8]).nibble_overflow.value
-    e2c_s = max_over_ranks(time.perf_counter() - t0)
-    chk_c = float(henv.buffers.rewards.sum())
+    ep_s, chk_p, bsum_p, _, _ = time_host_env(n_chunks=args.e2e_chunks, wire="plain")
+    e2e_plain = {"value": total_envs * Ke / ep_s, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,
+                 "steps": Ke, "ms_per_step": 1e3 * ep_s / Ke, "chunks": args.e2e_chunks, "checksum": chk_p,
+                 "boards_checksum": bsum_p,
+                 "api": "g2048_env_step_host, G2048_BOARDS_BYTES (16 bytes per board over PCIe, pinned host buffers)"}
+    e2c_s, chk_c, _, overflow, _ = time_host_env(n_chunks=args.e2e_chunks, board_format="nibble")
     e2e_compact = {"value": total_envs * Ke / e2c_s, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 13,
                    "steps": Ke, "ms_per_step": 1e3 * e2c_s / Ke, "boards_not_fitting": overflow, "checksum": chk_c,
                    "api": "g2048_env_step_host, G2048_BOARDS_NIBBLE (boards 4 bits per cell, pinned host buffers)"}
-    henv.close()
 
     if rank != 0:
         if world > 1:
@@ -741,9 +746,13 @@ def run_ours(args):
                                                "Chained launches of different env sets overlap on the GPU, so this is the rate at "
                                                "which launches complete; one chained launch running ALONE (as under ncu, which "
                                                "serialises launches) takes longer — profiles/r02_chain_launches_summary.md"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 21,
-                "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "chunks": args.e2e_chunks,
-                "api": "g2048_env_step_host (pinned host buffers)", "checksum": chk},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n * 13,
+                "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke, "chunks": args.e2e_chunks_packed or 4,
+                "api": "g2048_env_step_host, G2048_BOARDS_BYTES_PACKED_WIRE: pinned host buffers, boards [n,16] exponent bytes "
+                       "in the caller's array; on the wire 4 bits per cell, expanded inside the call by the library's host "
+                       "threads", "unpack_threads": args.unpack_threads or "library default (half the CPUs of the process, at most 8)",
+                "boards_not_fitting": e2e_overflow, "checksum": chk, "boards_checksum": bsum},
+        "e2e_plain_wire": e2e_plain,
         "e2e_compact": e2e_compact,
         "weak": weak,
         "plain_launches": plain,
@@ -798,6 +807,8 @@ def main():
     ap.add_argument("--fused-steps", type=int, default=32, help="steps per g2048_step_many launch (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-chunks", type=int, default=2)
+    ap.add_argument("--e2e-chunks-packed", type=int, default=0, help="slices of the default (packed-wire) host call; 0 = library default")
+    ap.add_argument("--unpack-threads", type=int, default=0, help="host threads of the packed-wire host call; 0 = library default")
     ap.add_argument("--ref-steps-per-proc", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 extra block (N = 1)")

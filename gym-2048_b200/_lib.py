@@ -86,7 +86,7 @@ class EnvConfig(C.Structure):
         ("device", C.c_int32), ("flags", C.c_uint32), ("n", C.c_uint64),
         ("env_id_base", C.c_uint64), ("seed", C.c_uint64),
         ("illegal_move_reward", C.c_float), ("max_tile_exp", C.c_uint32),
-        ("n_chunks", C.c_uint32), ("board_format", C.c_uint32),
+        ("n_chunks", C.c_uint32), ("board_format", C.c_uint32), ("unpack_threads", C.c_uint32),
     ]
 
 
@@ -99,7 +99,7 @@ class HostStepOut(C.Structure):
     ]
 
 
-BOARDS_BYTES, BOARDS_NIBBLE = 0, 1
+BOARDS_BYTES, BOARDS_NIBBLE, BOARDS_BYTES_PACKED_WIRE = 0, 1, 2
 
 
 def _stale():

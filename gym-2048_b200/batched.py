@@ -626,16 +626,23 @@ class HostSteppedEnv:
     full_boards() fetches the 16-byte boards."""
 
     def __init__(self, num_envs, seed=0, device=0, env_id_base=0, illegal_move_reward=0.0, max_tile=None,
-                 auto_reset=True, n_chunks=0, extras=False, board_format="bytes"):
+                 auto_reset=True, n_chunks=0, extras=False, board_format="bytes", wire="packed", unpack_threads=0):
         if board_format not in ("bytes", "nibble"):
             raise ValueError("board_format must be 'bytes' or 'nibble'")
+        if wire not in ("packed", "plain"):
+            raise ValueError("wire must be 'packed' or 'plain'")
         self.lib = _lib.lib()
         self.num_envs = int(num_envs)
         nibble = board_format == "nibble"
+        # board_format='bytes', wire='packed' (default): the caller still gets [n,16] exponent bytes, but they cross
+        # PCIe 4 bits per cell and `unpack_threads` host threads of the library (0 = half the CPUs of the process, at
+        # most 8) expand them slice by slice (G2048_BOARDS_BYTES_PACKED_WIRE); wire='plain' moves the 16 bytes.
+        self.wire = "packed" if (wire == "packed" and not nibble) else "plain"
+        fmt = _lib.BOARDS_NIBBLE if nibble else (_lib.BOARDS_BYTES_PACKED_WIRE if self.wire == "packed" else _lib.BOARDS_BYTES)
         cfg = _lib.EnvConfig(int(device), FLAG_AUTO_RESET if auto_reset else 0, self.num_envs, int(env_id_base),
                              int(seed) & (2**64 - 1), float(illegal_move_reward), tile_to_exp(max_tile),
-                             int(n_chunks), _lib.BOARDS_NIBBLE if nibble else _lib.BOARDS_BYTES)
-        self._n_chunks = min(int(n_chunks) if n_chunks else 2, 64)
+                             int(n_chunks), fmt, int(unpack_threads))
+        self._n_chunks = min(int(n_chunks) if n_chunks else (4 if self.wire == "packed" else 2), 64)
         self._h = C.c_void_p()
         check(self.lib.g2048_env_create(C.byref(self._h), C.byref(cfg)))
         self.buffers = HostBuffers(self.num_envs, extras, nibble)

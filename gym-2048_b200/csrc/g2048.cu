@@ -9,8 +9,18 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <new>
 
 #include "../../include/g2048.h"
@@ -1157,6 +1167,112 @@ int launch_check(const char* name) {
 // ------------------------------------------------------------------------------------
 }  // namespace g2048
 
+// ------------------------------------------------------------------------------------
+// G2048_BOARDS_BYTES_PACKED_WIRE: the host half.  The boards of a step arrive in pinned staging memory 4 bits per
+// cell, slice by slice; a small pool of host threads expands every slice into the caller's [n*16] byte array while
+// the next slice is still on the wire.  The pool sleeps between steps (condition variable) and spins within one.
+// ------------------------------------------------------------------------------------
+// 8 bytes -> 16 bytes per board: byte b of the packed board holds cells 2b (low nibble) and 2b+1 (high nibble).
+#ifndef G2048_UNPACK_NT       // 1: non-temporal stores into the caller's array.  Measured (profiles/r02_e2e_wire.log): SLOWER,
+#define G2048_UNPACK_NT 0    // 0.46 vs 0.34 ms per 1 Mi boards — with ordinary stores the caller's 16 MB array stays in the
+#endif                       // host's last-level cache from step to step and the expansion never waits for DRAM
+static void unpack_nibble_boards(const uint8_t* src, uint8_t* dst, size_t boards) {
+  size_t i = 0;
+#if defined(__SSE2__)
+  const __m128i low = _mm_set1_epi8(0x0F);
+  const bool aligned = G2048_UNPACK_NT && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+  for (; i + 2 <= boards; i += 2) {
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 8 * i));       // two boards
+    const __m128i lo = _mm_and_si128(x, low), hi = _mm_and_si128(_mm_srli_epi16(x, 4), low);
+    const __m128i b0 = _mm_unpacklo_epi8(lo, hi), b1 = _mm_unpackhi_epi8(lo, hi);
+    __m128i* out = reinterpret_cast<__m128i*>(dst + 16 * i);
+    if (aligned) { _mm_stream_si128(out, b0); _mm_stream_si128(out + 1, b1); }
+    else { _mm_storeu_si128(out, b0); _mm_storeu_si128(out + 1, b1); }
+  }
+  if (aligned) _mm_sfence();
+#endif
+  for (; i < boards; ++i)
+    for (int b = 0; b < 8; ++b) {
+      const uint8_t v = src[8 * i + b];
+      dst[16 * i + 2 * b] = v & 15u;
+      dst[16 * i + 2 * b + 1] = v >> 4;
+    }
+}
+
+struct UnpackPool {
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv;
+  uint64_t epoch = 0;                 // guarded by m: a new job is published by incrementing it
+  bool quit = false;                  // guarded by m
+  // the job of the current epoch (written by the stepping thread before the epoch is published)
+  const uint8_t* src = nullptr;
+  uint8_t* dst = nullptr;
+  uint64_t lo[64], cnt[64];
+  int n_slices = 0;
+  std::atomic<int> ready[64];         // slice c: 0 = still on the wire, 1 = in `src`, -1 = the step failed, give up
+  std::atomic<int> done{0};           // workers that are through with the current job
+
+  void run(int t, int T) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> hold(m);
+        cv.wait(hold, [&] { return quit || epoch != seen; });
+        if (quit) return;
+        seen = epoch;
+      }
+      for (int c = 0; c < n_slices; ++c) {
+        int r;
+        while ((r = ready[c].load(std::memory_order_acquire)) == 0) {
+#if defined(__SSE2__)
+          _mm_pause();
+#endif
+        }
+        if (r < 0) break;
+        // this worker's share of the slice, in pairs of boards
+        const uint64_t pairs = (cnt[c] + 1) / 2, a = pairs * t / T * 2, b = pairs * (t + 1) / T * 2;
+        const uint64_t hi = b < cnt[c] ? b : cnt[c];
+        if (a < hi) unpack_nibble_boards(src + 8 * (lo[c] + a), dst + 16 * (lo[c] + a), hi - a);
+      }
+      done.fetch_add(1, std::memory_order_release);
+    }
+  }
+  explicit UnpackPool(int T) {
+    for (int c = 0; c < 64; ++c) ready[c].store(0);
+    for (int t = 0; t < T; ++t) workers.emplace_back([this, t, T] { run(t, T); });
+  }
+  ~UnpackPool() {
+    { std::lock_guard<std::mutex> hold(m); quit = true; }
+    cv.notify_all();
+    for (std::thread& w : workers) w.join();
+  }
+  // Publish a job: every slice still on the wire.
+  void start(const uint8_t* s_, uint8_t* d_, int slices) {
+    src = s_; dst = d_; n_slices = slices;
+    for (int c = 0; c < slices; ++c) ready[c].store(0, std::memory_order_relaxed);
+    done.store(0, std::memory_order_relaxed);
+    { std::lock_guard<std::mutex> hold(m); ++epoch; }
+    cv.notify_all();
+  }
+  void finish() {                      // wait until every worker is through with the job
+    while (done.load(std::memory_order_acquire) != (int)workers.size()) std::this_thread::yield();
+  }
+  void abort_from(int c) {             // the step failed: release the workers from the slices that will never arrive
+    for (; c < n_slices; ++c) ready[c].store(-1, std::memory_order_release);
+  }
+};
+
+static int default_unpack_threads() {
+  int cpus = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);      // a rank pinned to 4 cores gets 2 threads, not 8
+#endif
+  int t = cpus / 2;
+  return t < 1 ? 1 : (t > 8 ? 8 : t);
+}
+
 struct G2048Env {
   G2048EnvConfig cfg;
   uint64_t step_index, reset_index;
@@ -1174,6 +1290,8 @@ struct G2048Env {
   uint8_t* d_nibble;            // [n*8] compact host format (cfg.board_format == G2048_BOARDS_NIBBLE)
   uint32_t* d_overflow;         // [64] per-slice counters of boards that do not fit the compact format
   uint32_t* h_overflow;         // pinned mirror of d_overflow
+  uint8_t* h_nibble;            // [n*8] pinned staging of the packed boards (cfg.board_format == G2048_BOARDS_BYTES_PACKED_WIRE)
+  UnpackPool* pool;             // the threads that expand them into the caller's array
   cudaStream_t streams[4];
   int n_streams;
   cudaEvent_t slice_done[64];   // slice c's kernel has finished (the small result copies wait for it on another stream)
@@ -1756,6 +1874,8 @@ int g2048_env_destroy(G2048Env* e) {
   cudaFree(e->d_illegal); cudaFree(e->d_highest); cudaFree(e->d_mask);
   cudaFree(e->d_ep_score); cudaFree(e->d_ep_len); cudaFree(e->d_nibble); cudaFree(e->d_overflow);
   if (e->h_overflow) cudaFreeHost(e->h_overflow);
+  delete e->pool;
+  if (e->h_nibble) cudaFreeHost(e->h_nibble);
   delete e;
   return G2048_OK;
 }
@@ -1764,13 +1884,17 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   if (!out || !cfg) return fail(G2048_ERR_INVALID, "g2048_env_create: NULL argument");
   if (cfg->n == 0) return fail(G2048_ERR_INVALID, "g2048_env_create: n must be > 0");
   if (cfg->max_tile_exp > 63u) return fail(G2048_ERR_INVALID, "g2048_env_create: max_tile_exp > 63");
-  if (cfg->board_format > G2048_BOARDS_NIBBLE) return fail(G2048_ERR_INVALID, "g2048_env_create: unknown board_format %u", cfg->board_format);
+  if (cfg->board_format > G2048_BOARDS_BYTES_PACKED_WIRE) return fail(G2048_ERR_INVALID, "g2048_env_create: unknown board_format %u", cfg->board_format);
+  if (cfg->unpack_threads > 64u) return fail(G2048_ERR_INVALID, "g2048_env_create: unpack_threads > 64");
   G2048_CUDA(cudaSetDevice(cfg->device));
   G2048Env* e = new (std::nothrow) G2048Env();
   if (!e) return fail(G2048_ERR_NOMEM, "g2048_env_create: out of host memory");
   std::memset(e, 0, sizeof *e);
   e->cfg = *cfg;
-  e->n_chunks = cfg->n_chunks ? cfg->n_chunks : 2u;
+  const bool packed_wire = cfg->board_format == G2048_BOARDS_BYTES_PACKED_WIRE;
+  // default pipeline depth: a 1/16 lead slice + the rest; with packed boards the rest in three slices, so that the
+  // expansion of a slice (host threads) hides behind the transfer of the next
+  e->n_chunks = cfg->n_chunks ? cfg->n_chunks : (packed_wire ? 4u : 2u);
   if (e->n_chunks > 64u) e->n_chunks = 64u;
   const uint64_t n = cfg->n;
   cudaError_t err = cudaSuccess;
@@ -1778,9 +1902,16 @@ int g2048_env_create(G2048Env** out, const G2048EnvConfig* cfg) {
   alloc((void**)&e->d_boards, n * 16); alloc((void**)&e->d_actions, n); alloc((void**)&e->d_rewards, n * 4);
   alloc((void**)&e->d_dones, n); alloc((void**)&e->d_illegal, n); alloc((void**)&e->d_highest, n);
   alloc((void**)&e->d_mask, n); alloc((void**)&e->d_ep_score, n * 4); alloc((void**)&e->d_ep_len, n * 4);
-  if (cfg->board_format == G2048_BOARDS_NIBBLE) {
+  if (cfg->board_format == G2048_BOARDS_NIBBLE || packed_wire) {
     alloc((void**)&e->d_nibble, n * 8); alloc((void**)&e->d_overflow, 64 * 4);
     if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_overflow, 64 * 4, cudaHostAllocDefault);
+  }
+  if (packed_wire) {
+    if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_nibble, n * 8, cudaHostAllocDefault);
+    if (err == cudaSuccess) {
+      e->pool = new (std::nothrow) UnpackPool(cfg->unpack_threads ? (int)cfg->unpack_threads : default_unpack_threads());
+      if (!e->pool) err = cudaErrorMemoryAllocation;
+    }
   }
   if (err == cudaSuccess) err = cudaMemset(e->d_ep_score, 0, n * 4);
   if (err == cudaSuccess) err = cudaMemset(e->d_ep_len, 0, n * 4);
@@ -1852,7 +1983,8 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   const uint64_t rest_chunks = lead ? e->n_chunks - 1 : e->n_chunks;
   uint64_t per = (n - lead + rest_chunks - 1) / rest_chunks;
   per = (per + 255) / 256 * 256;
-  const bool nibble = e->cfg.board_format == G2048_BOARDS_NIBBLE;
+  const bool packed_wire = e->cfg.board_format == G2048_BOARDS_BYTES_PACKED_WIRE;
+  const bool nibble = e->cfg.board_format == G2048_BOARDS_NIBBLE || packed_wire;      // what the kernel writes for the wire
 #ifndef G2048_E2E_SPLIT_COPIES   // 1: the small result arrays of a slice are copied on a second stream (another copy engine).
 #define G2048_E2E_SPLIT_COPIES 0   //    Measured (profiles/r02_e2e_sweep.log): no difference — the call is bound by the board
 #endif                             //    bytes over PCIe, not by per-copy set-up — so the simpler schedule ships.
@@ -1890,7 +2022,12 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
       G2048_CUDA(cudaStreamWaitEvent(aux, e->slice_done[c], 0));
       s2 = aux;
     }
-    if (nibble) {
+    if (packed_wire) {
+      // packed boards into the pinned staging area; the event tells the host threads that slice c may be expanded
+      G2048_CUDA(cudaMemcpyAsync(e->h_nibble + 8 * lo, e->d_nibble + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, s));
+      G2048_CUDA(cudaEventRecord(e->slice_done[c], s));
+      G2048_CUDA(cudaMemcpyAsync(e->h_overflow + c, e->d_overflow + c, 4, cudaMemcpyDeviceToHost, s));
+    } else if (nibble) {
       G2048_CUDA(cudaMemcpyAsync(o->boards + 8 * lo, e->d_nibble + 8 * lo, 8 * m, cudaMemcpyDeviceToHost, s));
       G2048_CUDA(cudaMemcpyAsync(e->h_overflow + c, e->d_overflow + c, 4, cudaMemcpyDeviceToHost, s2));
     } else {
@@ -1903,12 +2040,26 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     if (o->legal_mask) G2048_CUDA(cudaMemcpyAsync(o->legal_mask + lo, e->d_mask + lo, m, cudaMemcpyDeviceToHost, s2));
     return G2048_OK;
   };
+  if (packed_wire) {
+    // the slice plan for the host threads, before anything is in flight
+    int k = 0;
+    for (uint64_t lo = 0; lo < n; ++k) {
+      const uint64_t want = (k == 0 && lead) ? lead : per;
+      const uint64_t m = (n - lo < want) ? n - lo : want;
+      e->pool->lo[k] = lo;
+      e->pool->cnt[k] = m;
+      lo += m;
+    }
+    if (k > e->n_events) return fail(G2048_ERR_INVALID, "g2048_env_step_host: more slices than events");
+    e->pool->start(e->h_nibble, o->boards, k);
+  }
   int c = 0;
   for (uint64_t lo = 0; lo < n; ++c) {
     const uint64_t want = (c == 0 && lead) ? lead : per;
     const uint64_t m = (n - lo < want) ? n - lo : want;
     const int rc = issue_slice(lo, m, e->streams[c % (aux ? 3 : e->n_streams)], c);
     if (rc) {
+      if (packed_wire) { e->pool->abort_from(0); e->pool->finish(); }
       // Some slices of this step may already have run.  Drain the streams (no work of the failed call is left
       // in flight over the caller's host buffers) and say that the env is no longer at a step boundary: the
       // step index is NOT advanced and the boards are a mix of pre- and post-step slices — reset or
@@ -1922,11 +2073,29 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     lo += m;
   }
   e->step_index += 1;
+  if (packed_wire) {
+    // hand every slice to the host threads as it lands (they expand slice k while slice k+1 is on the wire)
+    for (int k = 0; k < c; ++k) {
+      const cudaError_t ev = cudaEventSynchronize(e->slice_done[k]);
+      if (ev != cudaSuccess) {
+        e->pool->abort_from(k);
+        e->pool->finish();
+        return cuda_fail(ev, "g2048_env_step_host: cudaEventSynchronize(slice)");
+      }
+      e->pool->ready[k].store(1, std::memory_order_release);
+    }
+  }
   const int rc = env_sync(e);
-  if (rc == G2048_OK && nibble && o->nibble_overflow) {
+  if (packed_wire) e->pool->finish();
+  if (rc == G2048_OK && nibble) {
     uint32_t total = 0;
     for (int k = 0; k < c; ++k) total += e->h_overflow[k];
-    *o->nibble_overflow = total;
+    if (o->nibble_overflow) *o->nibble_overflow = total;
+    if (packed_wire && total != 0) {
+      // some board holds a tile >= 65536 and does not fit 4 bits per cell: this step's boards again, in full
+      G2048_CUDA(cudaMemcpyAsync(o->boards, e->d_boards, n * 16, cudaMemcpyDeviceToHost, e->streams[0]));
+      G2048_CUDA(cudaStreamSynchronize(e->streams[0]));
+    }
   }
   return rc;
 }

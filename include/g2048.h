@@ -462,8 +462,10 @@ typedef struct G2048EnvConfig {
   float    illegal_move_reward;
   uint32_t max_tile_exp;
   uint32_t n_chunks;             /* copy/compute pipeline depth; 0 = library default (2: a 1/16 lead slice + the rest) */
-  uint32_t board_format;         /* G2048_BOARDS_BYTES (0) or G2048_BOARDS_NIBBLE: what g2048_env_step_host   */
-                                 /* writes to out->boards                                                      */
+  uint32_t board_format;         /* G2048_BOARDS_BYTES (0), _NIBBLE or _BYTES_PACKED_WIRE: what                */
+                                 /* g2048_env_step_host writes to out->boards and how it gets there            */
+  uint32_t unpack_threads;       /* G2048_BOARDS_BYTES_PACKED_WIRE: host threads that expand the boards;       */
+                                 /* 0 = library default (half the CPUs the process may run on, at most 8)      */
 } G2048EnvConfig;
 
 /* G2048EnvConfig.board_format.  The step is PCIe-bound for a host caller (21 bytes per board come back);  */
@@ -472,6 +474,11 @@ typedef struct G2048EnvConfig {
 /* out->nibble_overflow and g2048_env_get_boards_host returns the full 16-byte boards.                    */
 #define G2048_BOARDS_BYTES  0u
 #define G2048_BOARDS_NIBBLE 1u
+/* out->boards is [n*16] exponent bytes exactly as with G2048_BOARDS_BYTES, but the boards cross PCIe 4 bits per cell   */
+/* (13 instead of 21 bytes per board) and the library expands them into the caller's buffer with its own host threads,  */
+/* slice by slice, while the next slice is still on the wire.  A step in which some board holds a tile >= 65536 is      */
+/* detected (the kernel counts them) and its boards are fetched again in full: correct, at the plain format's speed.    */
+#define G2048_BOARDS_BYTES_PACKED_WIRE 2u
 
 /* Host result pointers for g2048_env_step_host; boards/rewards/dones required. */
 typedef struct G2048HostStepOut {

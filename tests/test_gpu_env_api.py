@@ -240,10 +240,11 @@ def test_vec_env_sb3_semantics(g, penalty):
     assert penalty == 0.0 or n_neg > 0
 
 
+@pytest.mark.parametrize("wire", ["packed", "plain"])    # packed (default): the boards cross PCIe 4 bits per cell
 @pytest.mark.parametrize("extras", [True, False])       # False: the O_EPRUN kernel bench.py's e2e leg runs
-def test_host_stepped_env_matches_oracle(g, extras):
+def test_host_stepped_env_matches_oracle(g, extras, wire):
     n = 20000
-    h = g.HostSteppedEnv(n, seed=9, n_chunks=3, extras=extras)
+    h = g.HostSteppedEnv(n, seed=9, n_chunks=3, extras=extras, wire=wire)
     o = oracle.OracleBatch(n, seed=9, threads=4)
     assert np.array_equal(h.reset().numpy(), o.reset())
     rng = np.random.default_rng(1)
@@ -294,6 +295,33 @@ def test_host_stepped_env_nibble_boards(g):
     assert np.array_equal(h.full_boards().numpy(), o.boards)
     assert np.array_equal(b.unpacked_boards().numpy()[7:], o.boards[7:])
     h.close()
+
+
+@pytest.mark.parametrize("n,n_chunks,threads", [(1, 0, 1), (255, 0, 3), (70001, 0, 0), (300000, 7, 5), (1 << 20, 0, 0)])
+def test_host_stepped_env_packed_wire_equals_plain_wire(g, n, n_chunks, threads):
+    """G2048_BOARDS_BYTES_PACKED_WIRE: [n,16] exponent bytes exactly as the plain format delivers them — odd sizes,
+    slice counts and thread counts — and a step with tiles >= 65,536 (which do not fit 4 bits) still comes back whole."""
+    a = g.HostSteppedEnv(n, seed=3, n_chunks=n_chunks, wire="packed", unpack_threads=threads)
+    b = g.HostSteppedEnv(n, seed=3, n_chunks=2, wire="plain")
+    assert a.wire == "packed" and b.wire == "plain"
+    assert np.array_equal(a.reset().numpy(), b.reset().numpy())
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        act = rng.integers(0, 4, n).astype(np.uint8)
+        ra, rb = a.step(act), b.step(act)
+        assert np.array_equal(ra.boards.numpy(), rb.boards.numpy()), t
+        assert np.array_equal(ra.rewards.numpy(), rb.rewards.numpy()) and np.array_equal(ra.dones.numpy(), rb.dones.numpy())
+        assert ra.nibble_overflow.value == 0
+    big = rb.boards.numpy().copy()
+    k = min(n, 5)
+    big[:k, 0], big[:k, 1], big[:k, 2:] = 16, 17, 0
+    for h in (a, b):
+        g._lib.check(h.lib.g2048_env_set_boards_host(h._h, big.ctypes.data))
+    act = np.full(n, 2, np.uint8)                      # Down: the big tiles stay on the board
+    ra, rb = a.step(act), b.step(act)
+    assert ra.nibble_overflow.value == k
+    assert np.array_equal(ra.boards.numpy(), rb.boards.numpy()) and int(ra.boards.numpy().max()) == 17
+    a.close(), b.close()
 
 
 def test_checkpoint_resume_is_exact(g):
@@ -362,8 +390,10 @@ def test_bench_prints_one_contract_line_on_a_small_workload():
     r = d["roofline"]
     assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic_kind"]
     assert abs(r["achieved"] - 38 * 65536 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
-    assert d["e2e"]["d2h_bytes_per_step"] == 65536 * 21 and d["e2e_compact"]["d2h_bytes_per_step"] == 65536 * 13
-    assert d["e2e"]["checksum"] == d["e2e_compact"]["checksum"]          # same rewards through both host formats
+    assert d["e2e"]["d2h_bytes_per_step"] == 65536 * 13 and d["e2e_compact"]["d2h_bytes_per_step"] == 65536 * 13
+    assert d["e2e_plain_wire"]["d2h_bytes_per_step"] == 65536 * 21
+    assert d["e2e"]["checksum"] == d["e2e_compact"]["checksum"] == d["e2e_plain_wire"]["checksum"]     # same rewards through every host format
+    assert d["e2e"]["boards_checksum"] == d["e2e_plain_wire"]["boards_checksum"]      # and the same boards, packed or plain on the wire
     # the Python-loop issue path (forced) steps the same boards: identical checksum
     d2 = run("--small-below", "0")
     assert "Python loop" in d2["timing"]["issue"] and d2["state_checksum"] == d["state_checksum"]
