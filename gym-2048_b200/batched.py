@@ -626,15 +626,18 @@ class HostSteppedEnv:
     full_boards() fetches the 16-byte boards."""
 
     def __init__(self, num_envs, seed=0, device=0, env_id_base=0, illegal_move_reward=0.0, max_tile=None,
-                 auto_reset=True, n_chunks=0, extras=False, board_format="bytes", wire="packed", unpack_threads=0):
+                 auto_reset=True, n_chunks=0, extras=False, board_format="bytes", wire="auto", unpack_threads=0):
         if board_format not in ("bytes", "nibble"):
             raise ValueError("board_format must be 'bytes' or 'nibble'")
-        if wire not in ("packed", "plain"):
-            raise ValueError("wire must be 'packed' or 'plain'")
+        if wire not in ("auto", "packed", "plain"):
+            raise ValueError("wire must be 'auto', 'packed' or 'plain'")
+        if wire == "auto":         # the expansion needs host threads: with fewer than 4 CPUs the plain wire is as fast
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            wire = "packed" if cpus >= 4 else "plain"
         self.lib = _lib.lib()
         self.num_envs = int(num_envs)
         nibble = board_format == "nibble"
-        # board_format='bytes', wire='packed' (default): the caller still gets [n,16] exponent bytes, but they cross
+        # board_format='bytes', wire='packed' (the default on a host with 4+ CPUs): the caller still gets [n,16] exponent bytes, but they cross
         # PCIe 4 bits per cell and `unpack_threads` host threads of the library (0 = half the CPUs of the process, at
         # most 8) expand them slice by slice (G2048_BOARDS_BYTES_PACKED_WIRE); wire='plain' moves the 16 bytes.
         self.wire = "packed" if (wire == "packed" and not nibble) else "plain"

@@ -1269,7 +1269,9 @@ static int default_unpack_threads() {
   cpu_set_t set;
   if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);      // a rank pinned to 4 cores gets 2 threads, not 8
 #endif
-  int t = cpus / 2;
+  // half the CPUs on a big host (the expansion is bound by the caches, not by instructions: eight threads are
+  // enough); all but one — the stepping thread spins on the slice events — on a small one
+  int t = cpus > 8 ? cpus / 2 : cpus - 1;
   return t < 1 ? 1 : (t > 8 ? 8 : t);
 }
 

@@ -465,7 +465,8 @@ typedef struct G2048EnvConfig {
   uint32_t board_format;         /* G2048_BOARDS_BYTES (0), _NIBBLE or _BYTES_PACKED_WIRE: what                */
                                  /* g2048_env_step_host writes to out->boards and how it gets there            */
   uint32_t unpack_threads;       /* G2048_BOARDS_BYTES_PACKED_WIRE: host threads that expand the boards;       */
-                                 /* 0 = library default (half the CPUs the process may run on, at most 8)      */
+                                 /* 0 = library default (half the CPUs the process may run on, at most 8;      */
+                                 /* all but one of them on hosts with 8 CPUs or fewer)                         */
 } G2048EnvConfig;
 
 /* G2048EnvConfig.board_format.  The step is PCIe-bound for a host caller (21 bytes per board come back);  */
