@@ -695,10 +695,12 @@ class HostSteppedEnv:
         slices, every slice rounded up to 256 boards."""
         n, chunks = self.num_envs, self._n_chunks
         lead = -(-(n // 16) // 256) * 256 if (chunks >= 2 and n >= 65536) else 0
-        rest = chunks - 1 if lead else chunks
-        per = -(-(n - lead) // rest)
+        tail = 0                                             # (the library's plain-tail experiment is off)
+        body = n - tail
+        rest = chunks - (1 if lead else 0) - (1 if tail else 0)
+        per = -(-(body - lead) // rest)
         per = -(-per // 256) * 256
-        return (1 if lead else 0) + -(-(n - lead) // per)
+        return (1 if lead else 0) + -(-(body - lead) // per) + (1 if tail else 0)
 
     @property
     def step_index(self):

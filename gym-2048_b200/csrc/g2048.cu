@@ -1980,13 +1980,27 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   // (profiles/r01_e2e_chunks.log: 1/16 lead + 2 slices 0.463 ms per 1 Mi boards, equal thirds 0.488 ms;
   //  profiles/r02_e2e_sweep.log: 1/16 lead + 1 slice 0.451 ms, + 2 slices 0.464 ms: the default is 2 chunks.)
   constexpr uint64_t lead_div = 16;
+  const bool packed_wire = e->cfg.board_format == G2048_BOARDS_BYTES_PACKED_WIRE;
   uint64_t lead = 0;
   if (e->n_chunks >= 2 && n >= 65536) lead = (n / lead_div + 255) / 256 * 256;
-  const uint64_t rest_chunks = lead ? e->n_chunks - 1 : e->n_chunks;
-  uint64_t per = (n - lead + rest_chunks - 1) / rest_chunks;
+  // Packed wire, experiment (off): the LAST 1/DIV of the boards travel as plain 16-byte boards straight into the
+  // caller's array — they need no expansion, and while they are on the wire the host threads could finish the packed
+  // slices.  Measured (profiles/r02_e2e_wire.log): slower for every DIV — 0.347 ms per 1 Mi boards without a plain
+  // tail, 0.366 / 0.370 / 0.375 / 0.411 with 1/12, 1/8, 1/6, 1/4 — the extra 8 bytes per board on the wire cost more
+  // than the expansion they save.
+#ifndef G2048_PACKED_PLAIN_TAIL_DIV
+#define G2048_PACKED_PLAIN_TAIL_DIV 0
+#endif
+  uint64_t tail = 0;
+  if (packed_wire && G2048_PACKED_PLAIN_TAIL_DIV && e->n_chunks >= 3 && n >= 65536)
+    tail = (n / (G2048_PACKED_PLAIN_TAIL_DIV ? G2048_PACKED_PLAIN_TAIL_DIV : 1) + 255) / 256 * 256;
+  const uint64_t n_body = n - tail;                                       // [0, n_body): lead + equal slices; [n_body, n): the tail
+  const uint64_t rest_chunks = e->n_chunks - (lead ? 1 : 0) - (tail ? 1 : 0);
+  uint64_t per = (n_body - lead + rest_chunks - 1) / rest_chunks;
   per = (per + 255) / 256 * 256;
-  const bool packed_wire = e->cfg.board_format == G2048_BOARDS_BYTES_PACKED_WIRE;
-  const bool nibble = e->cfg.board_format == G2048_BOARDS_NIBBLE || packed_wire;      // what the kernel writes for the wire
+  const bool packed_format = packed_wire;
+  const bool nibble_format = e->cfg.board_format == G2048_BOARDS_NIBBLE || packed_wire;      // what the kernel writes for the wire
+  const bool nibble = nibble_format;
 #ifndef G2048_E2E_SPLIT_COPIES   // 1: the small result arrays of a slice are copied on a second stream (another copy engine).
 #define G2048_E2E_SPLIT_COPIES 0   //    Measured (profiles/r02_e2e_sweep.log): no difference — the call is bound by the board
 #endif                             //    bytes over PCIe, not by per-copy set-up — so the simpler schedule ships.
@@ -1994,7 +2008,10 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   // follow the kernel on the auxiliary stream, so that their per-copy set-up cost runs beside the board copies
   // instead of between them.
   const cudaStream_t aux = (G2048_E2E_SPLIT_COPIES && e->n_streams == 4) ? e->streams[3] : nullptr;
-  auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s, int c) -> int {
+  auto issue_slice = [&](uint64_t lo, uint64_t m, cudaStream_t s, int c, bool plain_boards) -> int {
+    const bool nibble = nibble_format && !plain_boards;        // this slice's boards go out 4 bits per cell
+    const bool packed_wire = packed_format && !plain_boards;   // ... into the staging area, for the host threads
+    if (plain_boards && nibble_format) e->h_overflow[c] = 0;   // (nothing can overflow in a plain slice)
     if (nibble) G2048_CUDA(cudaMemsetAsync(e->d_overflow + c, 0, 4, s));
     G2048_CUDA(cudaMemcpyAsync(e->d_actions + lo, actions_host + lo, m, cudaMemcpyHostToDevice, s));
     G2048StepArgs a;
@@ -2045,9 +2062,9 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   if (packed_wire) {
     // the slice plan for the host threads, before anything is in flight
     int k = 0;
-    for (uint64_t lo = 0; lo < n; ++k) {
+    for (uint64_t lo = 0; lo < n_body; ++k) {
       const uint64_t want = (k == 0 && lead) ? lead : per;
-      const uint64_t m = (n - lo < want) ? n - lo : want;
+      const uint64_t m = (n_body - lo < want) ? n_body - lo : want;
       e->pool->lo[k] = lo;
       e->pool->cnt[k] = m;
       lo += m;
@@ -2055,11 +2072,14 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
     if (k > e->n_events) return fail(G2048_ERR_INVALID, "g2048_env_step_host: more slices than events");
     e->pool->start(e->h_nibble, o->boards, k);
   }
-  int c = 0;
+  int c = 0, n_packed = 0;
   for (uint64_t lo = 0; lo < n; ++c) {
-    const uint64_t want = (c == 0 && lead) ? lead : per;
-    const uint64_t m = (n - lo < want) ? n - lo : want;
-    const int rc = issue_slice(lo, m, e->streams[c % (aux ? 3 : e->n_streams)], c);
+    const bool in_tail = lo >= n_body;
+    const uint64_t want = in_tail ? tail : ((c == 0 && lead) ? lead : per);
+    const uint64_t end = in_tail ? n : n_body;
+    const uint64_t m = (end - lo < want) ? end - lo : want;
+    if (!in_tail) n_packed = c + 1;
+    const int rc = issue_slice(lo, m, e->streams[c % (aux ? 3 : e->n_streams)], c, in_tail);
     if (rc) {
       if (packed_wire) { e->pool->abort_from(0); e->pool->finish(); }
       // Some slices of this step may already have run.  Drain the streams (no work of the failed call is left
@@ -2077,7 +2097,7 @@ int g2048_env_step_host(G2048Env* e, const uint8_t* actions_host, const G2048Hos
   e->step_index += 1;
   if (packed_wire) {
     // hand every slice to the host threads as it lands (they expand slice k while slice k+1 is on the wire)
-    for (int k = 0; k < c; ++k) {
+    for (int k = 0; k < n_packed; ++k) {
       const cudaError_t ev = cudaEventSynchronize(e->slice_done[k]);
       if (ev != cudaSuccess) {
         e->pool->abort_from(k);

@@ -35,8 +35,8 @@ def main():
     print("cpus of the process: %d" % len(os.sched_getaffinity(0)))
     ms, ref = run(n, steps, wire="plain", n_chunks=2)
     print("plain wire   chunks 2             %.3f ms/step  %.3e steps/s" % (ms, n / ms * 1e3), flush=True)
-    for chunks in (2, 3, 4, 6):
-        for threads in (2, 4, 8):
+    for chunks in (0, 4, 5, 6):
+        for threads in (0, 4, 12):
             ms, chk = run(n, steps, wire="packed", n_chunks=chunks, unpack_threads=threads)
             print("packed wire  chunks %-2d threads %-2d  %.3f ms/step  %.3e steps/s  %s" % (
                 chunks, threads, ms, n / ms * 1e3, "boards identical" if chk == ref else "BOARDS DIFFER"), flush=True)
