@@ -30,6 +30,7 @@ EXPORTS = [
     "g2048_encode_obs", "g2048_values_from_exp", "g2048_exp_from_values", "g2048_philox", "g2048_philox2x32", "g2048_draw_words",
     "g2048_env_create", "g2048_env_destroy", "g2048_env_reset_host", "g2048_env_step_host",
     "g2048_env_device_ptrs", "g2048_env_set_boards_host", "g2048_env_get_boards_host", "g2048_env_step_index",
+    "g2048_unpack_boards_host",
     "g2048_sample_actions", "g2048_symmetry", "g2048_augment", "g2048_discounted_return", "g2048_gae",
     "g2048_csv_export", "g2048_csv_rows", "g2048_csv_import",
 ]
@@ -189,6 +190,7 @@ def lib():
     L.g2048_env_set_boards_host.argtypes = [vp, vp]
     L.g2048_env_get_boards_host.argtypes = [vp, vp]
     L.g2048_env_step_index.argtypes = [vp]
+    L.g2048_unpack_boards_host.argtypes = [vp, vp, C.c_uint64]
     L.g2048_sample_actions.argtypes = [vp, vp, u64, u64, u64, u64, vp]
     L.g2048_symmetry.argtypes = [vp, vp, vp, vp, vp, vp, u64, C.c_int, C.c_int, vp]
     L.g2048_augment.argtypes = [vp] * 5 + [u64] + [vp] * 6

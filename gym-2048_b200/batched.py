@@ -609,8 +609,8 @@ class HostBuffers:
         if not self.nibble:
             return self.boards
         out = torch.empty((self.boards.shape[0], 16), dtype=torch.uint8)
-        out[:, 0::2] = self.boards & 15
-        out[:, 1::2] = self.boards >> 4
+        check(_lib.lib().g2048_unpack_boards_host(C.c_void_p(self.boards.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                  self.boards.shape[0]))
         return out
 
 

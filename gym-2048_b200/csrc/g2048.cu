@@ -2130,6 +2130,13 @@ int g2048_env_get_boards_host(G2048Env* e, uint8_t* boards_host) {
   return G2048_OK;
 }
 
+int g2048_unpack_boards_host(const uint8_t* packed, uint8_t* boards, uint64_t n) {
+  if (n == 0) return G2048_OK;
+  if (!packed || !boards) return fail(G2048_ERR_INVALID, "g2048_unpack_boards_host: NULL argument");
+  unpack_nibble_boards(packed, boards, (size_t)n);
+  return G2048_OK;
+}
+
 int g2048_env_device_ptrs(G2048Env* e, uint8_t** boards, float** rewards, uint8_t** dones) {
   if (!e) return fail(G2048_ERR_INVALID, "g2048_env_device_ptrs: env is NULL");
   if (boards) *boards = e->d_boards;

@@ -507,6 +507,11 @@ int g2048_env_set_boards_host(G2048Env* env, const uint8_t* boards_host);
 int g2048_env_get_boards_host(G2048Env* env, uint8_t* boards_host);
 uint64_t g2048_env_step_index(const G2048Env* env);
 
+/* Host-only helper (no device involved): expand n boards from 4 bits per cell ([n*8], the layout of                 */
+/* G2048StepArgs.boards_nibble / G2048_BOARDS_NIBBLE) to one exponent byte per cell ([n*16]) — what the library's   */
+/* own threads do for G2048_BOARDS_BYTES_PACKED_WIRE, for a caller that took the packed boards.                     */
+int g2048_unpack_boards_host(const uint8_t* packed, uint8_t* boards, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,3 +202,20 @@ def test_bench_issue_plan_is_the_single_stream_schedule_per_env_set():
                 got.setdefault(s_, []).append(row)
         assert got == single
         assert sum(len(items) for items, _ in plan) == total
+
+
+def test_unpack_boards_host_is_the_nibble_layout():
+    """g2048_unpack_boards_host (what the library's threads run for G2048_BOARDS_BYTES_PACKED_WIRE): cell c of a board is
+    nibble c of its 8 packed bytes — odd counts (scalar tail), unaligned destinations, every nibble value."""
+    import numpy as np
+    L = g._lib.lib()
+    rng = np.random.default_rng(3)
+    for n, off in ((0, 0), (1, 0), (2, 0), (3, 1), (255, 0), (1000, 5), (65537, 16)):
+        boards = rng.integers(0, 16, (n, 16)).astype(np.uint8)
+        packed = (boards[:, 0::2] | (boards[:, 1::2] << 4)).astype(np.uint8)          # byte b = cells 2b (low), 2b+1 (high)
+        packed = np.ascontiguousarray(packed)
+        raw = np.zeros(n * 16 + off + 16, np.uint8)
+        out = raw[off:off + n * 16]
+        assert L.g2048_unpack_boards_host(packed.ctypes.data if n else None, out.ctypes.data if n else None, n) == 0
+        assert np.array_equal(out.reshape(n, 16), boards) and not raw[off + n * 16:].any() and not raw[:off].any()
+    assert L.g2048_unpack_boards_host(None, None, 4) == -1
