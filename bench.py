@@ -409,7 +409,7 @@ def time_step_regions_mt(torch, g, games, pool, spinup, W, K, R, T, barrier, max
     Returns (region times in ms; issue description; t_start, t_end; launches inside the timed regions)."""
     S, P = len(games), pool.shape[0]
     assert S % T == 0 and K % T == 0, "--sets and --steps must be multiples of the issuing threads"
-    total, Kt, St = spinup + W + R * K, K // T, S // T
+    total, Kt = spinup + W + R * K, K // T
     dev = games[0].device
     streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
     scheds, starts, evs = [], [], []
