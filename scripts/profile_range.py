@@ -2,7 +2,7 @@
 """A RANGE of overlapping chained launches under `ncu --replay-mode range` (cudaProfilerStart/Stop around one
 g2048_step_list call): pipe utilisation of the steady state, which a per-kernel capture cannot see (ncu serialises
 kernels; chained launches only reach their speed when several share the machine).
-    ncu --replay-mode range --metrics ... python scripts/profile_range.py [chained|plain] [n] [launches]"""
+    ncu --replay-mode range --metrics ... python scripts/profile_range.py [chained|plain|c4|c4_plain] [n] [launches]"""
 import os
 import sys
 
@@ -20,15 +20,18 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)
     pool = torch.randint(0, 4, (8, n), generator=gen, device=dev, dtype=torch.uint8)
     S = 32
-    games = [g.BatchedGame2048(n, seed=1, device=dev, env_id_base=s * n, outputs=()) for s in range(S)]
+    c4 = mode.startswith("c4")                   # BASELINE config 4: legal mask + random-legal policy drawn in the kernel
+    games = [g.BatchedGame2048(n, seed=1, device=dev, env_id_base=s * n, outputs=("legal_mask",) if c4 else ()) for s in range(S)]
     for gm in games:
         gm.reset()
-    chained = "interleaved" if mode == "chained" else False
+        if c4:
+            gm.step_many(policy="legal", n_steps=150)        # mid-game boards
+    chained = False if mode.endswith("plain") else "interleaved"
     warm, sched = g.StepSchedule(), g.StepSchedule()
     for j in range(128):
-        warm.add(games[j % S], pool[j % 8], chained=chained)
+        warm.add(games[j % S], None if c4 else pool[j % 8], policy="legal" if c4 else None, chained=chained)
     for j in range(launches):
-        sched.add(games[j % S], pool[j % 8], chained=chained)
+        sched.add(games[j % S], None if c4 else pool[j % 8], policy="legal" if c4 else None, chained=chained)
     sched.build()
     warm.run()
     torch.cuda.synchronize()
