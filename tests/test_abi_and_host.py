@@ -219,3 +219,36 @@ def test_unpack_boards_host_is_the_nibble_layout():
         assert L.g2048_unpack_boards_host(packed.ctypes.data if n else None, out.ctypes.data if n else None, n) == 0
         assert np.array_equal(out.reshape(n, 16), boards) and not raw[off + n * 16:].any() and not raw[:off].any()
     assert L.g2048_unpack_boards_host(None, None, 4) == -1
+
+
+def test_chain_state_machine_of_the_batched_class():
+    """BatchedGame2048._chain_args without a GPU: which launches carry the chain buffer, G2048_FLAG_CHAINED and
+    G2048_FLAG_CHAIN_INTERLEAVED — a chained step only chains to a step of the same chain, same mode, with nothing
+    else in between; plain steps are launched without the buffer."""
+    import torch
+    L = g._lib
+    game = g.BatchedGame2048.__new__(g.BatchedGame2048)
+    game.device, game._chain, game._chain_broken, game._chain_mode, game._step_counter = torch.device("cpu"), None, True, "direct", None
+
+    def flags(chained):
+        a = L.StepArgs()
+        a.flags = L.FLAG_AUTO_RESET
+        game._chain_args(a, chained)
+        return bool(a.chain), bool(a.flags & L.FLAG_CHAINED), bool(a.flags & L.FLAG_CHAIN_INTERLEAVED)
+    assert flags(False) == (False, False, False) and game._chain is None          # plain: no buffer is ever made
+    assert flags(True) == (True, False, False)                                    # first chained step: the head
+    assert game._chain.numel() == L.CHAIN_WORDS and int(game._chain.abs().sum()) == 0
+    assert flags(True) == (True, True, False) and flags(True) == (True, True, False)
+    assert flags("interleaved") == (True, False, True)                            # another launch shape: a head again
+    assert flags("interleaved") == (True, True, True)
+    assert flags(False) == (False, False, False)                                  # a plain step in between ...
+    assert flags("interleaved") == (True, False, True)                            # ... breaks the chain
+    assert flags("interleaved") == (True, True, True)
+    game._chain_broken = True                                                     # what reset / set_boards / step_many do
+    assert flags("interleaved") == (True, False, True)
+    game._step_counter = torch.zeros(2, dtype=torch.int64)                        # device-side step index: no chaining
+    assert flags(False) == (False, False, False)
+    with pytest.raises(g.G2048Error):
+        flags(True)
+    with pytest.raises(ValueError):
+        flags("sideways")
